@@ -1,0 +1,182 @@
+// a9/a10 — per-row elementwise epilogues between convolutions and the dense BEV scatter.
+//
+// Replaces
+//   nn.BatchNorm1d(eval) + nn.ReLU + residual add on `.features`   pcdet/models/backbones_3d/spconv_backbone.py:21-25,50-66
+//   SparseConvTensor.dense() used by HeightCompression.forward     pcdet/models/backbones_2d/map_to_bev/height_compression.py:21-23
+#include "common.cuh"
+
+namespace comb {
+namespace {
+
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p, size_t i);
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p, size_t i) { return __ldg(p + i); }
+template <>
+__device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) {
+  return __bfloat162float(p[i]);
+}
+template <typename T>
+__device__ __forceinline__ void st_from_float(T* p, size_t i, float v);
+template <>
+__device__ __forceinline__ void st_from_float<float>(float* p, size_t i, float v) { p[i] = v; }
+template <>
+__device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bfloat16* p, size_t i, float v) {
+  p[i] = __float2bfloat16(v);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) affine_relu_kernel(const T* __restrict__ x, int n_max,
+                                                           const int* __restrict__ n_dev, int C,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           const T* __restrict__ residual, int relu,
+                                                           T* __restrict__ out) {
+  const long long n = (long long)eff_n(n_max, n_dev) * C;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(e % C);
+    float v = ld_as_float(x, e);
+    if (scale) v = fmaf(v, __ldg(scale + c), __ldg(shift + c));
+    if (residual) v += ld_as_float(residual, e);
+    if (relu) v = fmaxf(v, 0.0f);
+    st_from_float(out, e, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__ x, int n_max,
+                                                        const int* __restrict__ n_dev, int C,
+                                                        __nv_bfloat16* __restrict__ out, int ld) {
+  const long long n = (long long)eff_n(n_max, n_dev) * ld;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int row = (int)(e / ld), c = (int)(e - (long long)row * ld);
+    out[e] = __float2bfloat16(c < C ? __ldg(x + (size_t)row * C + c) : 0.0f);
+  }
+}
+
+__global__ void __launch_bounds__(256) dense_index_kernel(const int4* __restrict__ coords, int n_max,
+                                                           const int* __restrict__ n_dev, int batch, int D, int H,
+                                                           int W, int* __restrict__ cell_row) {
+  const int n = eff_n(n_max, n_dev);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int4 c = __ldg(coords + i);
+    if (c.x < 0 || c.x >= batch || c.y < 0 || c.y >= D || c.z < 0 || c.z >= H || c.w < 0 || c.w >= W) continue;
+    cell_row[(((size_t)c.x * D + c.y) * H + c.z) * W + c.w] = i;
+  }
+}
+
+// Writes the WHOLE dense tensor: a block owns 32 consecutive cells of one frame (contiguous along x
+// in NCDHW for every channel), stages the present feature rows in shared memory (row-major, read
+// coalesced) and stores channel-major 128-byte lines.
+constexpr int kCells = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(256) dense_write_kernel(const T* __restrict__ feats,
+                                                           const int* __restrict__ cell_row, int C, int DHW,
+                                                           int tiles_per_frame, float* __restrict__ out) {
+  extern __shared__ float tile[];  // [kCells][C+1]
+  __shared__ int rows[kCells];
+  const int b = blockIdx.x / tiles_per_frame;
+  const int cell0 = (blockIdx.x - b * tiles_per_frame) * kCells;
+  const int tid = threadIdx.x;
+  int my = -1;
+  if (tid < kCells) {
+    int cell = cell0 + tid;
+    my = (cell < DHW) ? cell_row[(size_t)b * DHW + cell] : -1;
+    rows[tid] = my;
+  }
+  const int any = __syncthreads_or(my >= 0);
+  if (any) {
+    for (int e = tid; e < kCells * C; e += 256) {
+      int r = e / C, c = e - r * C;
+      int row = rows[r];
+      tile[r * (C + 1) + c] = row >= 0 ? ld_as_float(feats, (size_t)row * C + c) : 0.0f;
+    }
+    __syncthreads();
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+  const int cell = cell0 + lane;
+  if (cell >= DHW) return;
+  float* o = out + (size_t)b * C * DHW + cell;
+  for (int c = warp; c < C; c += 8) o[(size_t)c * DHW] = any ? tile[lane * (C + 1) + c] : 0.0f;
+}
+
+static int ew_grid(long long work) {
+  int g = cdiv(work, 256), cap = sm_count() * 16;
+  return g < cap ? (g > 0 ? g : 1) : cap;
+}
+
+}  // namespace
+}  // namespace comb
+
+using namespace comb;
+
+extern "C" int comb_affine_relu(const void* x, int dtype, int n_max, const int* n_dev, int C, const float* scale,
+                                const float* shift, const void* residual, int relu, void* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(n_max >= 0 && C >= 1, "comb_affine_relu: bad shape");
+  COMB_CHECK_ARG((scale == nullptr) == (shift == nullptr), "comb_affine_relu: scale and shift go together");
+  if (n_max == 0) return COMB_OK;
+  COMB_CHECK_ARG(x && out, "comb_affine_relu: null pointer");
+  int grid = ew_grid((long long)n_max * C);
+  if (dtype == COMB_DT_F32)
+    affine_relu_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, n_max, n_dev, C, scale, shift,
+                                                        (const float*)residual, relu, (float*)out);
+  else if (dtype == COMB_DT_BF16)
+    affine_relu_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, n_max, n_dev, C, scale, shift,
+                                                                (const __nv_bfloat16*)residual, relu,
+                                                                (__nv_bfloat16*)out);
+  else
+    COMB_CHECK_ARG(false, "comb_affine_relu: unknown dtype %d", dtype);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}
+
+extern "C" int comb_cast_pad(const float* x, int n_max, const int* n_dev, int C, void* out_bf16, int ld,
+                             void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(n_max >= 0 && C >= 1 && ld >= C, "comb_cast_pad: bad shape");
+  if (n_max == 0) return COMB_OK;
+  COMB_CHECK_ARG(x && out_bf16, "comb_cast_pad: null pointer");
+  cast_pad_kernel<<<ew_grid((long long)n_max * ld), 256, 0, stream>>>(x, n_max, n_dev, C, (__nv_bfloat16*)out_bf16, ld);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}
+
+extern "C" size_t comb_dense_workspace_bytes(int batch, int D, int H, int W) {
+  if (batch < 1 || D < 1 || H < 1 || W < 1) return 0;
+  return align_up((size_t)batch * D * H * W * 4, 256);
+}
+
+extern "C" int comb_dense(const void* feats, int dtype, const int* coords, int n_max, const int* n_dev, int batch,
+                          int C, int D, int H, int W, float* out, void* workspace, size_t workspace_bytes,
+                          void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(batch >= 1 && C >= 1 && D >= 1 && H >= 1 && W >= 1 && n_max >= 0, "comb_dense: bad shape");
+  COMB_CHECK_ARG(out && workspace, "comb_dense: null pointer");
+  COMB_CHECK_ARG(workspace_bytes >= comb_dense_workspace_bytes(batch, D, H, W), "comb_dense: workspace too small");
+  COMB_CHECK_ARG((long long)D * H * W < (1ll << 31) / 1, "comb_dense: frame volume too large");
+  const int DHW = D * H * W;
+  int* cell_row = (int*)workspace;
+  COMB_CUDA(cudaMemsetAsync(cell_row, 0xFF, (size_t)batch * DHW * 4, stream));
+  if (n_max > 0) {
+    COMB_CHECK_ARG(feats && coords, "comb_dense: null feats/coords");
+    dense_index_kernel<<<cdiv(n_max, 256), 256, 0, stream>>>((const int4*)coords, n_max, n_dev, batch, D, H, W,
+                                                             cell_row);
+    COMB_LAUNCH_CHECK();
+  }
+  const int tiles_per_frame = cdiv(DHW, kCells);
+  const long long blocks = (long long)tiles_per_frame * batch;
+  COMB_CHECK_ARG(blocks < (1ll << 31), "comb_dense: too many tiles");
+  size_t smem = (size_t)kCells * (C + 1) * sizeof(float);
+  COMB_CHECK_ARG(smem <= 48 * 1024, "comb_dense: C %d too large", C);
+  if (dtype == COMB_DT_F32)
+    dense_write_kernel<float><<<(unsigned)blocks, 256, smem, stream>>>((const float*)feats, cell_row, C, DHW,
+                                                                      tiles_per_frame, out);
+  else if (dtype == COMB_DT_BF16)
+    dense_write_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, smem, stream>>>((const __nv_bfloat16*)feats, cell_row,
+                                                                              C, DHW, tiles_per_frame, out);
+  else
+    COMB_CHECK_ARG(false, "comb_dense: unknown dtype %d", dtype);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}

@@ -1,0 +1,404 @@
+// a6 — coordinate hash table, strided-conv output set and gather-form rulebook.
+//
+// Replaces the indice-pair generation inside spconv's SubMConv3d / SparseConv3d forward, keyed by
+// `indice_key` at the call sites pcdet/models/backbones_3d/spconv_backbone.py:191-232.
+//
+//  * comb_hash_build      : key ((b*D+z)*H+y)*W+x -> row, 8-byte (key,row) slots, 64-bit CAS insert,
+//                           load factor <= 0.5, table L2 resident (<= 8 MB for 500k rows).
+//  * comb_conv_out_coords : output set of a strided conv as a BITMAP over the output grid
+//                           (atomicOr), popcount scan, then enumeration in ascending key order.
+//                           That order is the canonical row order (SURVEY hard part 1) and needs no sort.
+//  * comb_nbrmap_build    : nbr[k][o] = row of coordinate o*s - p + k*d  (probe of the input table).
+//                           One thread per (o, k) with o fastest: coalesced nbr stores; the 27 probes
+//                           of one output row hit at most 9 distinct L2 lines of the table.
+#include "common.cuh"
+
+namespace comb {
+namespace {
+
+struct Conv3 {
+  int k[3], s[3], p[3], d[3];  // z, y, x
+};
+
+__global__ void __launch_bounds__(256) hash_insert_kernel(const int4* __restrict__ coords, int n_max,
+                                                           const int* __restrict__ n_dev, int D, int H, int W,
+                                                           unsigned long long* __restrict__ table, uint32_t mask) {
+  const int n = eff_n(n_max, n_dev);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int4 c = __ldg(coords + i);  // (b, z, y, x)
+    uint32_t key = (uint32_t)(((c.x * D + c.y) * H + c.z) * W + c.w);
+    unsigned long long kv = ((unsigned long long)(uint32_t)i << 32) | key;  // little endian: .x = key, .y = row
+    uint32_t s = hash_u32(key) & mask;
+    while (true) {
+      unsigned long long prev = atomicCAS(table + s, 0xFFFFFFFFFFFFFFFFull, kv);
+      if (prev == 0xFFFFFFFFFFFFFFFFull) break;
+      if ((uint32_t)prev == key) break;  // duplicate coordinate: first writer wins
+      s = (s + 1) & mask;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) outset_mark_kernel(const int4* __restrict__ coords, int n_max,
+                                                           const int* __restrict__ n_dev, Conv3 cv, int oD, int oH,
+                                                           int oW, uint32_t* __restrict__ bitmap) {
+  const int n = eff_n(n_max, n_dev);
+  const int K = cv.k[0] * cv.k[1] * cv.k[2];
+  const long long total = (long long)n * K;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    int i = (int)(e / K), k = (int)(e - (long long)i * K);
+    int kx = k % cv.k[2], ky = (k / cv.k[2]) % cv.k[1], kz = k / (cv.k[2] * cv.k[1]);
+    int4 c = __ldg(coords + i);
+    int tz = c.y + cv.p[0] - kz * cv.d[0];
+    int ty = c.z + cv.p[1] - ky * cv.d[1];
+    int tx = c.w + cv.p[2] - kx * cv.d[2];
+    if (tz < 0 || ty < 0 || tx < 0) continue;
+    if (tz % cv.s[0] || ty % cv.s[1] || tx % cv.s[2]) continue;
+    int oz = tz / cv.s[0], oy = ty / cv.s[1], ox = tx / cv.s[2];
+    if (oz >= oD || oy >= oH || ox >= oW) continue;
+    uint32_t key = (uint32_t)(((c.x * oD + oz) * oH + oy) * oW + ox);
+    uint32_t bit = 1u << (key & 31);
+    uint32_t* w = bitmap + (key >> 5);
+    if (!(*((volatile uint32_t*)w) & bit)) atomicOr(w, bit);
+  }
+}
+
+// popcount scan over bitmap words, 3 phases (block sums of 4096 words, scan of sums, enumerate)
+constexpr int kWordsPerBlock = 4096;
+
+__global__ void __launch_bounds__(256) outset_blocksum_kernel(const uint32_t* __restrict__ bitmap, int nwords,
+                                                               int* __restrict__ block_sums) {
+  int base = blockIdx.x * kWordsPerBlock;
+  int s = 0;
+  for (int j = threadIdx.x; j < kWordsPerBlock; j += 256) {
+    int w = base + j;
+    if (w < nwords) s += __popc(bitmap[w]);
+  }
+  __shared__ int red[8];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    block_sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(1024) outset_scan_kernel(int* __restrict__ block_sums, int nblocks, int out_cap,
+                                                            int* __restrict__ out_count) {
+  // single block: exclusive scan of the per-block popcounts, 1024 at a time with a running carry
+  __shared__ int warp_tot[32];
+  __shared__ int s_running;
+  if (threadIdx.x == 0) s_running = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+    int b = b0 + threadIdx.x;
+    int v = b < nblocks ? block_sums[b] : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane], wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += t;
+      }
+      warp_tot[lane] = wi - w;
+    }
+    __syncthreads();
+    const int excl = s_running + warp_tot[warp] + incl - v;
+    if (b < nblocks) block_sums[b] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_running = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int total = s_running;
+    *out_count = total < out_cap ? total : out_cap;
+  }
+}
+
+__global__ void __launch_bounds__(256) outset_emit_kernel(const uint32_t* __restrict__ bitmap, int nwords,
+                                                           const int* __restrict__ block_offsets, int oD, int oH,
+                                                           int oW, int out_cap, int4* __restrict__ out_coords) {
+  // each warp owns 32 consecutive words per step -> warp-level scan of popcounts
+  __shared__ int s_off;
+  const int base = blockIdx.x * kWordsPerBlock;
+  if (threadIdx.x == 0) s_off = block_offsets[blockIdx.x];
+  __syncthreads();
+  __shared__ int warp_tot[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j0 = 0; j0 < kWordsPerBlock; j0 += 256) {
+    int w = base + j0 + threadIdx.x;
+    uint32_t bits = (w < nwords) ? bitmap[w] : 0u;
+    int v = __popc(bits), incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int woff = 0, round_tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int t = warp_tot[i];
+      if (i < warp) woff += t;
+      round_tot += t;
+    }
+    int pos = s_off + woff + incl - v;
+    while (bits) {
+      int bpos = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if (pos < out_cap) {
+        uint32_t key = ((uint32_t)w << 5) | (uint32_t)bpos;
+        int x = key % oW;
+        uint32_t r = key / oW;
+        int y = r % oH;
+        r /= oH;
+        int z = r % oD;
+        int b = r / oD;
+        out_coords[pos] = make_int4(b, z, y, x);
+      }
+      ++pos;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_off += round_tot;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) nbrmap_kernel(const int4* __restrict__ out_coords, int no_max,
+                                                      const int* __restrict__ no_dev, const uint2* __restrict__ table,
+                                                      uint32_t mask, int batch, int iD, int iH, int iW, Conv3 cv,
+                                                      int* __restrict__ nbr, int ld) {
+  const int no = eff_n(no_max, no_dev);
+  const int K = cv.k[0] * cv.k[1] * cv.k[2];
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= no) return;
+  const int4 c = __ldg(out_coords + o);
+  const int bz = c.y * cv.s[0] - cv.p[0], by = c.z * cv.s[1] - cv.p[1], bx = c.w * cv.s[2] - cv.p[2];
+  int k = 0;
+  for (int kz = 0; kz < cv.k[0]; ++kz) {
+    const int z = bz + kz * cv.d[0];
+    for (int ky = 0; ky < cv.k[1]; ++ky) {
+      const int y = by + ky * cv.d[1];
+      for (int kx = 0; kx < cv.k[2]; ++kx, ++k) {
+        const int x = bx + kx * cv.d[2];
+        int row = -1;
+        if (z >= 0 && z < iD && y >= 0 && y < iH && x >= 0 && x < iW) {
+          uint32_t key = (uint32_t)(((c.x * iD + z) * iH + y) * iW + x);
+          row = hash_lookup(table, mask, key);
+        }
+        nbr[(size_t)k * ld + o] = row;
+      }
+    }
+  }
+  (void)K;
+  (void)batch;
+}
+
+__global__ void __launch_bounds__(256) nbr_transpose_kernel(const int* __restrict__ nbr, int K, int no_max,
+                                                             const int* __restrict__ no_dev, int ld,
+                                                             int* __restrict__ nbr_t, int ni_max, int ld_t) {
+  const int no = eff_n(no_max, no_dev);
+  const long long total = (long long)K * no;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(e / no), o = (int)(e - (long long)k * no);
+    int i = nbr[(size_t)k * ld + o];
+    if (i >= 0 && i < ni_max) nbr_t[(size_t)k * ld_t + i] = o;
+  }
+}
+
+// One block per kernel offset: ordered compaction (ascending out row) by block-wide scan.
+__global__ void __launch_bounds__(1024) nbr_pairs_kernel(const int* __restrict__ nbr, int K, int no_max,
+                                                          const int* __restrict__ no_dev, int ld,
+                                                          int* __restrict__ pairs, int* __restrict__ pair_num) {
+  __shared__ int warp_tot[32];
+  __shared__ int s_run;
+  const int no = eff_n(no_max, no_dev);
+  const int k = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int* pin = pairs + (size_t)k * ld;
+  int* pout = pairs + (size_t)(K + k) * ld;
+  if (threadIdx.x == 0) s_run = 0;
+  __syncthreads();
+  for (int o0 = 0; o0 < no; o0 += 1024) {
+    int o = o0 + threadIdx.x;
+    int i = (o < no) ? nbr[(size_t)k * ld + o] : -1;
+    unsigned bal = __ballot_sync(0xffffffffu, i >= 0);
+    int wrank = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+      int t = warp_tot[w];
+      if (w < warp) woff += t;
+      tot += t;
+    }
+    int run = s_run;
+    if (i >= 0) {
+      pin[run + woff + wrank] = i;
+      pout[run + woff + wrank] = o;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_run = run + tot;
+    __syncthreads();
+  }
+  int total = s_run;
+  for (int j = total + threadIdx.x; j < ld; j += 1024) {
+    pin[j] = -1;
+    pout[j] = -1;
+  }
+  if (threadIdx.x == 0) pair_num[k] = total;
+}
+
+static int fill_conv3(Conv3& cv, const int* ksize, const int* stride, const int* pad, const int* dil) {
+  for (int j = 0; j < 3; ++j) {
+    cv.k[j] = ksize[j];
+    cv.s[j] = stride ? stride[j] : 1;
+    cv.p[j] = pad ? pad[j] : 0;
+    cv.d[j] = dil ? dil[j] : 1;
+    if (cv.k[j] < 1 || cv.s[j] < 1 || cv.p[j] < 0 || cv.d[j] < 1) return -1;
+  }
+  return 0;
+}
+
+static int check_volume(const char* who, int batch, int D, int H, int W) {
+  unsigned long long vol = (unsigned long long)batch * D * H * W;
+  if (batch < 1 || D < 1 || H < 1 || W < 1) {
+    set_error("%s: bad grid %d x (%d,%d,%d)", who, batch, D, H, W);
+    return COMB_EINVAL;
+  }
+  if (vol >= 0xFFFFFFFFull) {
+    set_error("%s: batch*volume %llu exceeds the 32-bit key space", who, vol);
+    return COMB_ERANGE;
+  }
+  return COMB_OK;
+}
+
+}  // namespace
+}  // namespace comb
+
+using namespace comb;
+
+extern "C" int comb_hash_slots(int n_max) {
+  unsigned s = 1024;
+  while (s < 2ull * (unsigned)(n_max > 0 ? n_max : 0)) s <<= 1;
+  return (int)s;
+}
+
+extern "C" int comb_hash_build(const int* coords, int n_max, const int* n_dev, int batch, int D, int H, int W,
+                               void* table, int slots, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(n_max >= 0 && table, "comb_hash_build: bad arguments");
+  COMB_CHECK_ARG(slots >= 2 * n_max && (slots & (slots - 1)) == 0, "comb_hash_build: slots %d must be a power of two >= 2*n (%d)", slots, n_max);
+  int rc = check_volume("comb_hash_build", batch, D, H, W);
+  if (rc) return rc;
+  COMB_CUDA(cudaMemsetAsync(table, 0xFF, (size_t)slots * 8, stream));
+  if (n_max == 0) return COMB_OK;
+  COMB_CHECK_ARG(coords, "comb_hash_build: null coords");
+  int grid = cdiv(n_max, 256);
+  hash_insert_kernel<<<grid, 256, 0, stream>>>((const int4*)coords, n_max, n_dev, D, H, W,
+                                               (unsigned long long*)table, (uint32_t)slots - 1);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}
+
+extern "C" size_t comb_outcoords_workspace_bytes(int batch, int oD, int oH, int oW) {
+  if (batch < 1 || oD < 1 || oH < 1 || oW < 1) return 0;
+  unsigned long long vol = (unsigned long long)batch * oD * oH * oW;
+  size_t nwords = (size_t)((vol + 31) / 32);
+  size_t nblocks = (nwords + kWordsPerBlock - 1) / kWordsPerBlock;
+  return align_up(nwords * 4, 256) + align_up(nblocks * 4, 256);
+}
+
+extern "C" int comb_conv_out_coords(const int* in_coords, int n_max, const int* n_dev, int batch, int oD, int oH,
+                                    int oW, const int* ksize, const int* stride, const int* pad, const int* dil,
+                                    int* out_coords, int out_cap, int* out_count, void* workspace,
+                                    size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(ksize && out_coords && out_count && workspace && out_cap >= 0, "comb_conv_out_coords: null pointer");
+  Conv3 cv;
+  COMB_CHECK_ARG(fill_conv3(cv, ksize, stride, pad, dil) == 0, "comb_conv_out_coords: bad conv parameters");
+  int rc = check_volume("comb_conv_out_coords", batch, oD, oH, oW);
+  if (rc) return rc;
+  COMB_CHECK_ARG(workspace_bytes >= comb_outcoords_workspace_bytes(batch, oD, oH, oW),
+                 "comb_conv_out_coords: workspace too small");
+  unsigned long long vol = (unsigned long long)batch * oD * oH * oW;
+  int nwords = (int)((vol + 31) / 32);
+  int nblocks = cdiv(nwords, kWordsPerBlock);
+  uint32_t* bitmap = (uint32_t*)workspace;
+  int* block_sums = (int*)((char*)workspace + align_up((size_t)nwords * 4, 256));
+  COMB_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)nwords * 4, stream));
+  if (n_max > 0) {
+    COMB_CHECK_ARG(in_coords, "comb_conv_out_coords: null in_coords");
+    const int K = cv.k[0] * cv.k[1] * cv.k[2];
+    long long work = (long long)n_max * K;
+    int grid = cdiv(work, 256);
+    int cap = sm_count() * 32;
+    grid = grid < cap ? grid : cap;
+    outset_mark_kernel<<<grid, 256, 0, stream>>>((const int4*)in_coords, n_max, n_dev, cv, oD, oH, oW, bitmap);
+    COMB_LAUNCH_CHECK();
+  }
+  outset_blocksum_kernel<<<nblocks, 256, 0, stream>>>(bitmap, nwords, block_sums);
+  COMB_LAUNCH_CHECK();
+  outset_scan_kernel<<<1, 1024, 0, stream>>>(block_sums, nblocks, out_cap, out_count);
+  COMB_LAUNCH_CHECK();
+  outset_emit_kernel<<<nblocks, 256, 0, stream>>>(bitmap, nwords, block_sums, oD, oH, oW, out_cap, (int4*)out_coords);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}
+
+extern "C" int comb_nbrmap_build(const int* out_coords, int no_max, const int* no_dev, const void* in_table,
+                                 int in_slots, int batch, int iD, int iH, int iW, const int* ksize, const int* stride,
+                                 const int* pad, const int* dil, int* nbr, int ld, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(ksize && in_table && nbr && ld >= no_max && no_max >= 0, "comb_nbrmap_build: bad arguments");
+  COMB_CHECK_ARG(in_slots > 0 && (in_slots & (in_slots - 1)) == 0, "comb_nbrmap_build: slots must be a power of two");
+  Conv3 cv;
+  COMB_CHECK_ARG(fill_conv3(cv, ksize, stride, pad, dil) == 0, "comb_nbrmap_build: bad conv parameters");
+  int rc = check_volume("comb_nbrmap_build", batch, iD, iH, iW);
+  if (rc) return rc;
+  if (no_max == 0) return COMB_OK;
+  COMB_CHECK_ARG(out_coords, "comb_nbrmap_build: null out_coords");
+  nbrmap_kernel<<<cdiv(no_max, 256), 256, 0, stream>>>((const int4*)out_coords, no_max, no_dev,
+                                                       (const uint2*)in_table, (uint32_t)in_slots - 1, batch, iD, iH,
+                                                       iW, cv, nbr, ld);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}
+
+extern "C" int comb_nbrmap_transpose(const int* nbr, int K, int no_max, const int* no_dev, int ld, int* nbr_t,
+                                     int ni_max, int ld_t, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(nbr_t && K >= 1 && ld_t >= ni_max && ld >= no_max, "comb_nbrmap_transpose: bad arguments");
+  COMB_CUDA(cudaMemsetAsync(nbr_t, 0xFF, (size_t)K * ld_t * 4, stream));
+  if (no_max == 0 || ni_max == 0) return COMB_OK;
+  COMB_CHECK_ARG(nbr, "comb_nbrmap_transpose: null nbr");
+  long long work = (long long)K * no_max;
+  int grid = cdiv(work, 256), cap = sm_count() * 32;
+  grid = grid < cap ? grid : cap;
+  nbr_transpose_kernel<<<grid, 256, 0, stream>>>(nbr, K, no_max, no_dev, ld, nbr_t, ni_max, ld_t);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}
+
+extern "C" int comb_nbrmap_to_pairs(const int* nbr, int K, int no_max, const int* no_dev, int ld, int* pairs,
+                                    int* pair_num, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(nbr && pairs && pair_num && K >= 1 && ld >= no_max, "comb_nbrmap_to_pairs: bad arguments");
+  nbr_pairs_kernel<<<K, 1024, 0, stream>>>(nbr, K, no_max, no_dev, ld, pairs, pair_num);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}

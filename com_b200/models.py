@@ -1,0 +1,280 @@
+"""Reference-facing model modules of the hot path, built on com_b200.sparse / com_b200.ops.
+
+Mirrors (same class names, constructor arguments, batch_dict keys and state_dict keys):
+  MeanVFE              pcdet/models/backbones_3d/vfe/mean_vfe.py:6-31
+  SparseBasicBlock,
+  post_act_block,
+  VoxelResBackBone8x   pcdet/models/backbones_3d/spconv_backbone.py:8-66,183-293
+  HeightCompression    pcdet/models/backbones_2d/map_to_bev/height_compression.py:4-26
+
+VoxelResBackBone8x has two execution modes:
+  * module mode (training, or `fused=False`): conv -> BatchNorm1d -> ReLU as separate modules exactly
+    like the reference, every conv a libcomb200 call with autograd support;
+  * fused mode (eval): one pre-planned chain of tensor-core convolutions in bf16 with the eval-mode
+    BatchNorm affine, bias, residual add and ReLU folded into each conv's epilogue, device-side row
+    counts (no host sync until the end), rulebooks shared between convs of one resolution.
+"""
+from functools import partial
+
+import torch
+from torch import nn
+
+from . import ops
+from . import sparse as spconv
+from .sparse import SparseConvTensor
+
+
+class _Cfg(dict):
+    """Tiny stand-in for the EasyDict configs the reference passes (attribute + .get access)."""
+    __getattr__ = dict.get
+
+
+class MeanVFE(nn.Module):
+    def __init__(self, model_cfg=None, num_point_features=5, **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg
+        self.num_point_features = num_point_features
+
+    def get_output_feature_dim(self):
+        return self.num_point_features
+
+    def forward(self, batch_dict, **kwargs):
+        """voxels (M,T,C), voxel_num_points (M,) -> voxel_features (M,C) = sum_t / max(num,1)"""
+        voxels, num = batch_dict['voxels'], batch_dict['voxel_num_points']
+        batch_dict['voxel_features'] = ops.mean_vfe(voxels.contiguous().float(), num.contiguous())
+        return batch_dict
+
+
+def post_act_block(in_channels, out_channels, kernel_size, indice_key=None, stride=1, padding=0, conv_type='subm',
+                   norm_fn=None):
+    if conv_type == 'subm':
+        conv = spconv.SubMConv3d(in_channels, out_channels, kernel_size, bias=False, indice_key=indice_key)
+    elif conv_type == 'spconv':
+        conv = spconv.SparseConv3d(in_channels, out_channels, kernel_size, stride=stride, padding=padding, bias=False,
+                                   indice_key=indice_key)
+    elif conv_type == 'inverseconv':
+        conv = spconv.SparseInverseConv3d(in_channels, out_channels, kernel_size, indice_key=indice_key, bias=False)
+    else:
+        raise NotImplementedError
+    return spconv.SparseSequential(conv, norm_fn(out_channels), nn.ReLU())
+
+
+class SparseBasicBlock(spconv.SparseModule):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, norm_fn=None, downsample=None, indice_key=None):
+        super().__init__()
+        assert norm_fn is not None
+        self.conv1 = spconv.SubMConv3d(inplanes, planes, kernel_size=3, stride=stride, padding=1, bias=True,
+                                       indice_key=indice_key)
+        self.bn1 = norm_fn(planes)
+        self.relu = nn.ReLU()
+        self.conv2 = spconv.SubMConv3d(planes, planes, kernel_size=3, stride=stride, padding=1, bias=True,
+                                       indice_key=indice_key)
+        self.bn2 = norm_fn(planes)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        identity = x
+        out = self.conv1(x)
+        out = out.replace_feature(self.relu(self.bn1(out.features)))
+        out = self.conv2(out)
+        out = out.replace_feature(self.bn2(out.features))
+        if self.downsample is not None:
+            identity = self.downsample(x)
+        return out.replace_feature(self.relu(out.features + identity.features))
+
+
+class VoxelResBackBone8x(nn.Module):
+    def __init__(self, model_cfg, input_channels, grid_size, fused=True, **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg if model_cfg is not None else _Cfg()
+        norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
+        grid_size = [int(g) for g in grid_size]
+        self.sparse_shape = [grid_size[2] + 1, grid_size[1], grid_size[0]]
+        self.fused = fused
+        block = post_act_block
+        self.conv_input = spconv.SparseSequential(
+            spconv.SubMConv3d(input_channels, 16, 3, padding=1, bias=False, indice_key='subm1'),
+            norm_fn(16), nn.ReLU())
+        self.conv1 = spconv.SparseSequential(
+            SparseBasicBlock(16, 16, norm_fn=norm_fn, indice_key='res1'),
+            SparseBasicBlock(16, 16, norm_fn=norm_fn, indice_key='res1'))
+        self.conv2 = spconv.SparseSequential(
+            block(16, 32, 3, norm_fn=norm_fn, stride=2, padding=1, indice_key='spconv2', conv_type='spconv'),
+            SparseBasicBlock(32, 32, norm_fn=norm_fn, indice_key='res2'),
+            SparseBasicBlock(32, 32, norm_fn=norm_fn, indice_key='res2'))
+        self.conv3 = spconv.SparseSequential(
+            block(32, 64, 3, norm_fn=norm_fn, stride=2, padding=1, indice_key='spconv3', conv_type='spconv'),
+            SparseBasicBlock(64, 64, norm_fn=norm_fn, indice_key='res3'),
+            SparseBasicBlock(64, 64, norm_fn=norm_fn, indice_key='res3'))
+        self.conv4 = spconv.SparseSequential(
+            block(64, 128, 3, norm_fn=norm_fn, stride=2, padding=(0, 1, 1), indice_key='spconv4', conv_type='spconv'),
+            SparseBasicBlock(128, 128, norm_fn=norm_fn, indice_key='res4'),
+            SparseBasicBlock(128, 128, norm_fn=norm_fn, indice_key='res4'))
+        last_pad = self.model_cfg.get('last_pad', 0) if hasattr(self.model_cfg, 'get') else 0
+        self.conv_out = spconv.SparseSequential(
+            spconv.SparseConv3d(128, 128, (3, 1, 1), stride=(2, 1, 1), padding=last_pad, bias=False,
+                                indice_key='spconv_down2'),
+            norm_fn(128), nn.ReLU())
+        self.num_point_features = 128
+        self.backbone_channels = {'x_conv1': 16, 'x_conv2': 32, 'x_conv3': 64, 'x_conv4': 128}
+        self._plan = None
+        self._ratios = {}
+
+    # ------------------------------------------------------------------ reference-shaped forward
+    def forward(self, batch_dict):
+        feats, coords = batch_dict['voxel_features'], batch_dict['voxel_coords']
+        batch_size = batch_dict['batch_size']
+        if self.fused and not self.training and not torch.is_grad_enabled():
+            x1, x2, x3, x4, out = self.forward_fused(feats, coords.int(), batch_size)
+        else:
+            x = SparseConvTensor(features=feats, indices=coords.int(), spatial_shape=self.sparse_shape,
+                                 batch_size=batch_size)
+            x = self.conv_input(x)
+            x1 = self.conv1(x)
+            x2 = self.conv2(x1)
+            x3 = self.conv3(x2)
+            x4 = self.conv4(x3)
+            out = self.conv_out(x4)
+        batch_dict.update({
+            'encoded_spconv_tensor': out, 'encoded_spconv_tensor_stride': 8,
+            'multi_scale_3d_features': {'x_conv1': x1, 'x_conv2': x2, 'x_conv3': x3, 'x_conv4': x4},
+            'multi_scale_3d_strides': {'x_conv1': 1, 'x_conv2': 2, 'x_conv3': 4, 'x_conv4': 8},
+        })
+        return batch_dict
+
+    # ------------------------------------------------------------------ fused eval path
+    def _fold(self, conv, bn):
+        """packed bf16 weight + per-channel (scale, shift) of conv-bias + eval BatchNorm1d."""
+        with torch.no_grad():
+            w3 = conv.weight.detach().reshape(conv.out_channels, -1, conv.in_channels).contiguous().float()
+            scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float()
+            shift = (bn.bias - bn.running_mean * scale).float()
+            if conv.bias is not None:
+                shift = shift + conv.bias.float() * scale
+            return dict(w=ops.pack_weight_bf16(w3), K=w3.shape[1], cout=conv.out_channels, conv=conv,
+                        scale=scale.contiguous(), shift=shift.contiguous())
+
+    def _plan_key(self):
+        return tuple(t._version for t in list(self.parameters()) + list(self.buffers())) + \
+            (next(self.parameters()).device,)
+
+    def _get_plan(self):
+        key = self._plan_key()
+        if self._plan is None or self._plan[0] != key:
+            p = {'input': self._fold(self.conv_input[0], self.conv_input[1])}
+            for li, stage in enumerate((self.conv1, self.conv2, self.conv3, self.conv4), start=1):
+                mods = list(stage._modules.values())
+                if li > 1:
+                    p['down%d' % li] = self._fold(mods[0][0], mods[0][1])
+                    mods = mods[1:]
+                p['res%d' % li] = [(self._fold(b.conv1, b.bn1), self._fold(b.conv2, b.bn2)) for b in mods]
+            p['out'] = self._fold(self.conv_out[0], self.conv_out[1])
+            self._plan = (key, p)
+        return self._plan[1]
+
+    @staticmethod
+    def _conv(x, spec, nbr, n_dev, residual=None):
+        return ops.spconv_fwd_bf16(x, spec['w'], spec['K'], spec['cout'], nbr, scale=spec['scale'],
+                                   shift=spec['shift'], residual=residual, relu=True, no_dev=n_dev)
+
+    def _run_fused(self, feats, coords, batch_size, caps):
+        plan = self._get_plan()
+        dev = feats.device
+        n1 = int(coords.shape[0])
+        if feats.dtype == torch.bfloat16 and feats.shape[1] == 16:
+            x = feats.contiguous()
+        else:
+            x = ops.cast_pad(feats.float().contiguous(), 16)
+        k3, one, zero = [3, 3, 3], [1, 1, 1], [0, 0, 0]
+        shape = list(self.sparse_shape)
+        cur_coords, cur_n = coords.contiguous(), None
+        levels = []
+        counts = []
+        for li in (1, 2, 3, 4):
+            if li > 1:
+                spec = plan['down%d' % li]
+                conv = spec['conv']
+                oshape = ops.conv_out_shape(shape, conv.kernel_size, conv.stride, conv.padding, conv.dilation)
+                ocoords, ocnt = ops.conv_out_coords(cur_coords, batch_size, oshape, conv.kernel_size, conv.stride,
+                                                    conv.padding, conv.dilation, caps[li], n_dev=cur_n)
+                nbr_d = ops.nbrmap_build(ocoords, table, slots, batch_size, shape, conv.kernel_size, conv.stride,
+                                         conv.padding, conv.dilation, no_dev=ocnt)
+                x = self._conv(x, spec, nbr_d, ocnt)
+                cur_coords, cur_n, shape = ocoords, ocnt, oshape
+                counts.append(ocnt)
+            table, slots = ops.hash_build(cur_coords, batch_size, shape, n_dev=cur_n)
+            nbr = ops.nbrmap_build(cur_coords, table, slots, batch_size, shape, k3, one, one, one, no_dev=cur_n)
+            if li == 1:
+                x = self._conv(x, plan['input'], nbr, cur_n)
+            for (c1, c2) in plan['res%d' % li]:
+                y = self._conv(x, c1, nbr, cur_n)
+                x = self._conv(y, c2, nbr, cur_n, residual=x)
+            levels.append((x, cur_coords, list(shape)))
+        spec = plan['out']
+        conv = spec['conv']
+        oshape = ops.conv_out_shape(shape, conv.kernel_size, conv.stride, conv.padding, conv.dilation)
+        ocoords, ocnt = ops.conv_out_coords(cur_coords, batch_size, oshape, conv.kernel_size, conv.stride,
+                                            conv.padding, conv.dilation, caps[5], n_dev=cur_n)
+        nbr_d = ops.nbrmap_build(ocoords, table, slots, batch_size, shape, conv.kernel_size, conv.stride,
+                                 conv.padding, conv.dilation, no_dev=ocnt)
+        x = self._conv(x, spec, nbr_d, ocnt)
+        counts.append(ocnt)
+        levels.append((x, ocoords, list(oshape)))
+        return levels, torch.cat(counts)
+
+    def _caps(self, n1, batch_size, worst):
+        """Row capacities of levels 2..4 and the output level for this call."""
+        shape = list(self.sparse_shape)
+        caps, prev = {}, n1
+        convs = [self.conv2[0][0], self.conv3[0][0], self.conv4[0][0], self.conv_out[0]]
+        for li, conv in zip((2, 3, 4, 5), convs):
+            shape = ops.conv_out_shape(shape, conv.kernel_size, conv.stride, conv.padding, conv.dilation)
+            vol = batch_size * shape[0] * shape[1] * shape[2]
+            contrib = 1
+            for kk, ss in zip(conv.kernel_size, conv.stride):
+                contrib *= (kk + ss - 1) // ss
+            hard = min(vol, prev * contrib)
+            r = self._ratios.get(li)
+            cap = hard if (worst or r is None) else min(hard, int(r * 1.25 * n1) + 1024)
+            caps[li] = max(cap, 1)
+            prev = caps[li]
+        return caps
+
+    def forward_fused(self, feats, coords, batch_size):
+        """-> (x_conv1, x_conv2, x_conv3, x_conv4, out) SparseConvTensors with bf16 features."""
+        if not feats.is_cuda:
+            raise RuntimeError("VoxelResBackBone8x needs CUDA tensors (no CPU fallback)")
+        n1 = int(coords.shape[0])
+        caps = self._caps(n1, batch_size, worst=False)
+        levels, counts = self._run_fused(feats, coords, batch_size, caps)
+        cnt = counts.tolist()                      # the only host sync of the fused path
+        if any(c >= caps[li] for c, li in zip(cnt, (2, 3, 4, 5))):
+            caps = self._caps(n1, batch_size, worst=True)
+            levels, counts = self._run_fused(feats, coords, batch_size, caps)
+            cnt = counts.tolist()
+        for c, li in zip(cnt, (2, 3, 4, 5)):
+            self._ratios[li] = max(self._ratios.get(li, 0.0), c / max(n1, 1))
+        ns = [n1] + cnt
+        outs = []
+        for (x, c, shape), n in zip(levels, ns):
+            outs.append(SparseConvTensor(x[:n], c[:n], shape, batch_size))
+        return tuple(outs)
+
+
+class HeightCompression(nn.Module):
+    def __init__(self, model_cfg=None, **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg if model_cfg is not None else _Cfg(NUM_BEV_FEATURES=256)
+        self.num_bev_features = self.model_cfg.NUM_BEV_FEATURES if hasattr(self.model_cfg, 'NUM_BEV_FEATURES') \
+            else self.model_cfg['NUM_BEV_FEATURES']
+
+    def forward(self, batch_dict):
+        """encoded_spconv_tensor -> spatial_features (N, C*D, H, W)"""
+        dense = batch_dict['encoded_spconv_tensor'].dense()
+        n, c, d, h, w = dense.shape
+        batch_dict['spatial_features'] = dense.view(n, c * d, h, w)
+        batch_dict['spatial_features_stride'] = batch_dict['encoded_spconv_tensor_stride']
+        return batch_dict

@@ -1,0 +1,392 @@
+"""Torch-facing functional wrappers over the C-ABI (device pointers + current stream).
+
+PyTorch is plumbing here: it owns device memory and the stream; all arithmetic happens in
+libcomb200.so.  Every function raises if a tensor is not a contiguous CUDA tensor — there is no
+CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DT_BF16, DT_F32, EPI_AFFINE, EPI_BIAS, EPI_RELU, EPI_RESIDUAL, check, int3
+
+__all__ = [
+    "voxelize", "mean_vfe", "hash_build", "conv_out_coords", "conv_out_shape", "nbrmap_build",
+    "nbrmap_transpose", "nbrmap_to_pairs", "spconv_fwd_f32", "spconv_dgrad_f32", "spconv_wgrad_f32",
+    "pack_weight_bf16", "spconv_fwd_bf16", "affine_relu", "cast_pad", "dense", "points_in_boxes_mask",
+    "points_in_boxes_index", "boxes_bev", "nms", "box_trig_host", "box_trig4_host",
+]
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need(t, dtype, name):
+    if t is None:
+        return
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (libcomb200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise RuntimeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return DT_F32
+    if t.dtype == torch.bfloat16:
+        return DT_BF16
+    raise RuntimeError("unsupported dtype %s" % t.dtype)
+
+
+# --------------------------------------------------------------------------------------------- voxelization
+def voxelize(points, frame_offsets, vsize_xyz, range_xyz, max_points, max_voxels, want_voxels=True,
+             mean_dtype=None, mean_c0=0, mean_ld=None):
+    """Batched hard voxelization (+ optional fused MeanVFE).  See comb_voxelize in include/comb200.h.
+
+    points: (N_total, C) fp32 CUDA, frames concatenated; frame_offsets: python ints, len batch+1.
+    Returns dict(voxels, coords (cap,4) b,z,y,x, num_points, counts (batch+1) device int32, mean).
+    Rows >= counts[-1] of every output are undefined.
+    """
+    lib = _lib.load()
+    _need(points, torch.float32, "points")
+    batch = len(frame_offsets) - 1
+    n_total, C = int(points.shape[0]), int(points.shape[1])
+    assert frame_offsets[-1] == n_total, "frame_offsets[-1] must equal the number of points"
+    dev = points.device
+    cap = batch * max_voxels
+    voxels = torch.empty((cap, max_points, C), dtype=torch.float32, device=dev) if want_voxels else None
+    coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    num = torch.empty((cap,), dtype=torch.int32, device=dev)
+    counts = torch.empty((batch + 1,), dtype=torch.int32, device=dev)
+    mean = None
+    mdt = DT_F32
+    if mean_dtype is not None:
+        mean_ld = mean_ld or (C - mean_c0)
+        mean = torch.empty((cap, mean_ld), dtype=mean_dtype, device=dev)
+        mdt = _dt(mean)
+    ws_bytes = lib.comb_voxelize_workspace_bytes(n_total, batch, max_voxels, max_points)
+    ws = _ws(ws_bytes, dev)
+    offs = (ctypes.c_int * (batch + 1))(*[int(x) for x in frame_offsets])
+    vs = (ctypes.c_float * 3)(*[float(np.float32(x)) for x in vsize_xyz])
+    rg = (ctypes.c_float * 6)(*[float(np.float32(x)) for x in range_xyz])
+    check(lib.comb_voxelize(_p(points), offs, batch, C, vs, rg, int(max_points), int(max_voxels), _p(voxels),
+                            _p(coords), _p(num), _p(mean), mdt, int(mean_c0), int(mean_ld or 1), _p(counts), _p(ws),
+                            ws.numel(), _stream()), "comb_voxelize")
+    return dict(voxels=voxels, coords=coords, num_points=num, counts=counts, mean=mean)
+
+
+def mean_vfe(voxels, num_points):
+    lib = _lib.load()
+    _need(voxels, torch.float32, "voxels")
+    M, T, C = voxels.shape
+    if num_points.dtype == torch.float32:
+        is_f = 1
+    elif num_points.dtype == torch.int32:
+        is_f = 0
+    else:
+        num_points, is_f = num_points.to(torch.int32), 0
+    _need(num_points, num_points.dtype, "num_points")
+    out = torch.empty((M, C), dtype=torch.float32, device=voxels.device)
+    check(lib.comb_mean_vfe(_p(voxels), _p(num_points), is_f, M, T, C, _p(out), _stream()), "comb_mean_vfe")
+    return out
+
+
+# --------------------------------------------------------------------------------------------- rulebook
+def hash_build(coords, batch, shape, n_dev=None):
+    """Hash table over (b,z,y,x) rows. Returns (table uint8 tensor, slots)."""
+    lib = _lib.load()
+    _need(coords, torch.int32, "coords")
+    _need(n_dev, torch.int32, "n_dev")
+    n = int(coords.shape[0])
+    slots = lib.comb_hash_slots(n)
+    table = torch.empty((slots * 8,), dtype=torch.uint8, device=coords.device)
+    D, H, W = [int(x) for x in shape]
+    check(lib.comb_hash_build(_p(coords), n, _p(n_dev), int(batch), D, H, W, _p(table), slots, _stream()),
+          "comb_hash_build")
+    return table, slots
+
+
+def conv_out_shape(in_shape, ksize, stride, pad, dil):
+    return [(int(i) + 2 * p - d * (k - 1) - 1) // s + 1 for i, k, s, p, d in zip(in_shape, ksize, stride, pad, dil)]
+
+
+def conv_out_coords(in_coords, batch, out_shape, ksize, stride, pad, dil, out_cap, n_dev=None):
+    """Canonical (ascending key) output coordinate set of a strided conv.
+    Returns (out_coords (out_cap,4) int32, out_count device int32[1])."""
+    lib = _lib.load()
+    _need(in_coords, torch.int32, "in_coords")
+    _need(n_dev, torch.int32, "n_dev")
+    dev = in_coords.device
+    oD, oH, oW = [int(x) for x in out_shape]
+    ws = _ws(lib.comb_outcoords_workspace_bytes(int(batch), oD, oH, oW), dev)
+    out = torch.empty((int(out_cap), 4), dtype=torch.int32, device=dev)
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+    check(lib.comb_conv_out_coords(_p(in_coords), int(in_coords.shape[0]), _p(n_dev), int(batch), oD, oH, oW,
+                                   int3(ksize), int3(stride), int3(pad), int3(dil), _p(out), int(out_cap), _p(cnt),
+                                   _p(ws), ws.numel(), _stream()), "comb_conv_out_coords")
+    return out, cnt
+
+
+def nbrmap_build(out_coords, table, slots, batch, in_shape, ksize, stride, pad, dil, no_dev=None, ld=None):
+    """Gather-form rulebook nbr (K, ld) int32; nbr[k, o] = input row or -1."""
+    lib = _lib.load()
+    _need(out_coords, torch.int32, "out_coords")
+    _need(no_dev, torch.int32, "no_dev")
+    no = int(out_coords.shape[0])
+    ld = int(ld or no)
+    K = int(ksize[0]) * int(ksize[1]) * int(ksize[2])
+    nbr = torch.empty((K, ld), dtype=torch.int32, device=out_coords.device)
+    iD, iH, iW = [int(x) for x in in_shape]
+    check(lib.comb_nbrmap_build(_p(out_coords), no, _p(no_dev), _p(table), int(slots), int(batch), iD, iH, iW,
+                                int3(ksize), int3(stride), int3(pad), int3(dil), _p(nbr), ld, _stream()),
+          "comb_nbrmap_build")
+    return nbr
+
+
+def nbrmap_transpose(nbr, ni, no_dev=None):
+    lib = _lib.load()
+    _need(nbr, torch.int32, "nbr")
+    K, ld = int(nbr.shape[0]), int(nbr.shape[1])
+    nbr_t = torch.empty((K, int(ni)), dtype=torch.int32, device=nbr.device)
+    check(lib.comb_nbrmap_transpose(_p(nbr), K, ld, _p(no_dev), ld, _p(nbr_t), int(ni), int(ni), _stream()),
+          "comb_nbrmap_transpose")
+    return nbr_t
+
+
+def nbrmap_to_pairs(nbr, no_dev=None):
+    """spconv-style (2, K, ld) pair lists and (K,) pair counts."""
+    lib = _lib.load()
+    _need(nbr, torch.int32, "nbr")
+    K, ld = int(nbr.shape[0]), int(nbr.shape[1])
+    pairs = torch.empty((2, K, ld), dtype=torch.int32, device=nbr.device)
+    num = torch.empty((K,), dtype=torch.int32, device=nbr.device)
+    check(lib.comb_nbrmap_to_pairs(_p(nbr), K, ld, _p(no_dev), ld, _p(pairs), _p(num), _stream()),
+          "comb_nbrmap_to_pairs")
+    return pairs, num
+
+
+# --------------------------------------------------------------------------------------------- sparse conv
+def _epi_flags(bias, scale, shift, residual, relu):
+    f = 0
+    if bias is not None:
+        f |= EPI_BIAS
+    if scale is not None:
+        assert shift is not None
+        f |= EPI_AFFINE
+    if residual is not None:
+        f |= EPI_RESIDUAL
+    if relu:
+        f |= EPI_RELU
+    return f
+
+
+def spconv_fwd_f32(feats, weight, nbr, bias=None, scale=None, shift=None, residual=None, relu=False, no_dev=None,
+                   no=None):
+    """weight: (Cout, K, Cin) fp32. feats (Ni, Cin) fp32 -> (No, Cout) fp32."""
+    lib = _lib.load()
+    _need(feats, torch.float32, "feats")
+    _need(weight, torch.float32, "weight")
+    _need(nbr, torch.int32, "nbr")
+    for n_, t_ in (("bias", bias), ("scale", scale), ("shift", shift), ("residual", residual)):
+        _need(t_, torch.float32, n_)
+    Cout, K, Cin = [int(x) for x in weight.shape]
+    assert int(feats.shape[1]) == Cin and int(nbr.shape[0]) == K
+    ld = int(nbr.shape[1])
+    no = ld if no is None else int(no)
+    out = torch.empty((no, Cout), dtype=torch.float32, device=feats.device)
+    check(lib.comb_spconv_fwd_f32(_p(feats), Cin, _p(weight), K, Cout, _p(nbr), ld, no, _p(no_dev),
+                                  _epi_flags(bias, scale, shift, residual, relu), _p(bias), _p(scale), _p(shift),
+                                  _p(residual), _p(out), _stream()), "comb_spconv_fwd_f32")
+    return out
+
+
+def spconv_dgrad_f32(dout, weight, nbr_t, ni_dev=None):
+    lib = _lib.load()
+    _need(dout, torch.float32, "dout")
+    _need(weight, torch.float32, "weight")
+    _need(nbr_t, torch.int32, "nbr_t")
+    Cout, K, Cin = [int(x) for x in weight.shape]
+    ni = int(nbr_t.shape[1])
+    din = torch.empty((ni, Cin), dtype=torch.float32, device=dout.device)
+    check(lib.comb_spconv_dgrad_f32(_p(dout), Cout, _p(weight), K, Cin, _p(nbr_t), ni, ni, _p(ni_dev), _p(din),
+                                    _stream()), "comb_spconv_dgrad_f32")
+    return din
+
+
+def spconv_wgrad_f32(feats, dout, nbr, no_dev=None):
+    lib = _lib.load()
+    _need(feats, torch.float32, "feats")
+    _need(dout, torch.float32, "dout")
+    _need(nbr, torch.int32, "nbr")
+    K, ld = int(nbr.shape[0]), int(nbr.shape[1])
+    Cin, Cout = int(feats.shape[1]), int(dout.shape[1])
+    dw = torch.empty((Cout, K, Cin), dtype=torch.float32, device=feats.device)
+    check(lib.comb_spconv_wgrad_f32(_p(feats), Cin, _p(dout), Cout, K, _p(nbr), ld, int(dout.shape[0]), _p(no_dev),
+                                    _p(dw), _stream()), "comb_spconv_wgrad_f32")
+    return dw
+
+
+def pad16(c):
+    for p in (16, 32, 64, 128):
+        if c <= p:
+            return p
+    raise RuntimeError("channel count %d > 128 not supported by the tensor-core path" % c)
+
+
+def pack_weight_bf16(weight):
+    """(Cout, K, Cin) fp32 -> pre-swizzled bf16 shared-memory image (uint8 tensor)."""
+    lib = _lib.load()
+    _need(weight, torch.float32, "weight")
+    Cout, K, Cin = [int(x) for x in weight.shape]
+    cin_p = pad16(Cin)
+    nbytes = lib.comb_spconv_packed_bytes(cin_p, K, Cout)
+    if nbytes == 0:
+        raise RuntimeError("unsupported conv shape for the bf16 path: Cin=%d Cout=%d K=%d" % (Cin, Cout, K))
+    out = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device)
+    check(lib.comb_spconv_pack_weight_bf16(_p(weight), Cout, K, Cin, cin_p, _p(out), _stream()),
+          "comb_spconv_pack_weight_bf16")
+    return out
+
+
+def spconv_fwd_bf16(feats, wpacked, K, Cout, nbr, bias=None, scale=None, shift=None, residual=None, relu=False,
+                    no_dev=None, no=None, out_dtype=torch.bfloat16, out=None):
+    """feats (Ni, Cin_p) bf16 with Cin_p in {16,32,64,128}; returns (No, Cout) bf16/fp32."""
+    lib = _lib.load()
+    _need(feats, torch.bfloat16, "feats")
+    _need(nbr, torch.int32, "nbr")
+    _need(residual, torch.bfloat16, "residual")
+    for n_, t_ in (("bias", bias), ("scale", scale), ("shift", shift)):
+        _need(t_, torch.float32, n_)
+    cin_p = int(feats.shape[1])
+    ld = int(nbr.shape[1])
+    no = ld if no is None else int(no)
+    if out is None:
+        out = torch.empty((no, Cout), dtype=out_dtype, device=feats.device)
+    check(lib.comb_spconv_fwd_bf16(_p(feats), cin_p, _p(wpacked), int(K), int(Cout), _p(nbr), ld, no, _p(no_dev),
+                                   _epi_flags(bias, scale, shift, residual, relu), _p(bias), _p(scale), _p(shift),
+                                   _p(residual), _p(out), _dt(out), _stream()), "comb_spconv_fwd_bf16")
+    return out
+
+
+def affine_relu(x, scale=None, shift=None, residual=None, relu=True, n_dev=None, out=None):
+    lib = _lib.load()
+    _need(x, x.dtype, "x")
+    n, C = int(x.shape[0]), int(x.shape[1])
+    out = torch.empty_like(x) if out is None else out
+    check(lib.comb_affine_relu(_p(x), _dt(x), n, _p(n_dev), C, _p(scale), _p(shift), _p(residual), int(bool(relu)),
+                               _p(out), _stream()), "comb_affine_relu")
+    return out
+
+
+def cast_pad(x, ld, n_dev=None):
+    lib = _lib.load()
+    _need(x, torch.float32, "x")
+    n, C = int(x.shape[0]), int(x.shape[1])
+    out = torch.empty((n, int(ld)), dtype=torch.bfloat16, device=x.device)
+    check(lib.comb_cast_pad(_p(x), n, _p(n_dev), C, _p(out), int(ld), _stream()), "comb_cast_pad")
+    return out
+
+
+def dense(feats, coords, batch, shape, n_dev=None):
+    """SparseConvTensor.dense(): (batch, C, D, H, W) fp32, fully written."""
+    lib = _lib.load()
+    _need(feats, feats.dtype, "feats")
+    _need(coords, torch.int32, "coords")
+    D, H, W = [int(x) for x in shape]
+    n, C = int(feats.shape[0]), int(feats.shape[1])
+    out = torch.empty((int(batch), C, D, H, W), dtype=torch.float32, device=feats.device)
+    ws = _ws(lib.comb_dense_workspace_bytes(int(batch), D, H, W), feats.device)
+    check(lib.comb_dense(_p(feats), _dt(feats), _p(coords), n, _p(n_dev), int(batch), C, D, H, W, _p(out), _p(ws),
+                         ws.numel(), _stream()), "comb_dense")
+    return out
+
+
+# --------------------------------------------------------------------------------------------- box ops
+def box_trig_host(boxes_np):
+    """(nb,2) float32 = (cosf(-rz), sinf(-rz)) from the host libm (bit-identical to the reference's)."""
+    lib = _lib.load()
+    b = np.ascontiguousarray(boxes_np, dtype=np.float32)
+    out = np.empty((b.shape[0], 2), dtype=np.float32)
+    lib.comb_box_trig_host(b.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), b.shape[0],
+                           out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    return out
+
+
+def box_trig4_host(boxes_np):
+    lib = _lib.load()
+    b = np.ascontiguousarray(boxes_np, dtype=np.float32)
+    out = np.empty((b.shape[0], 4), dtype=np.float32)
+    lib.comb_box_trig4_host(b.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), b.shape[0],
+                            out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    return out
+
+
+def points_in_boxes_mask(points, boxes, trig, out=None):
+    """points (P, >=3) fp32 CUDA (row stride = points.shape[1]), boxes (Nb,7), trig (Nb,2) -> (Nb,P) int32."""
+    lib = _lib.load()
+    _need(points, torch.float32, "points")
+    _need(boxes, torch.float32, "boxes")
+    _need(trig, torch.float32, "trig")
+    P, nb = int(points.shape[0]), int(boxes.shape[0])
+    if out is None:
+        out = torch.empty((nb, P), dtype=torch.int32, device=points.device)
+    check(lib.comb_points_in_boxes_mask(_p(points), P, int(points.shape[1]), _p(boxes), _p(trig), nb, _p(out),
+                                        _stream()), "comb_points_in_boxes_mask")
+    return out
+
+
+def points_in_boxes_index(points, boxes, out=None):
+    """points (B,P,3), boxes (B,T,7) -> (B,P) int32 first-hit index or -1."""
+    lib = _lib.load()
+    _need(points, torch.float32, "points")
+    _need(boxes, torch.float32, "boxes")
+    B, P, T = int(points.shape[0]), int(points.shape[1]), int(boxes.shape[1])
+    if out is None:
+        out = torch.empty((B, P), dtype=torch.int32, device=points.device)
+    _need(out, torch.int32, "out")
+    check(lib.comb_points_in_boxes_index(_p(points), _p(boxes), B, P, T, _p(out), _stream()),
+          "comb_points_in_boxes_index")
+    return out
+
+
+def boxes_bev(boxes_a, boxes_b, flavour="gpu", what="iou", trig_a=None, trig_b=None, out=None):
+    lib = _lib.load()
+    _need(boxes_a, torch.float32, "boxes_a")
+    _need(boxes_b, torch.float32, "boxes_b")
+    _need(trig_a, torch.float32, "trig_a")
+    _need(trig_b, torch.float32, "trig_b")
+    na, nb = int(boxes_a.shape[0]), int(boxes_b.shape[0])
+    if out is None:
+        out = torch.empty((na, nb), dtype=torch.float32, device=boxes_a.device)
+    _need(out, torch.float32, "out")
+    check(lib.comb_boxes_bev(_p(boxes_a), _p(trig_a), na, _p(boxes_b), _p(trig_b), nb,
+                             0 if flavour == "cpu" else 1, 0 if what == "iou" else 1, _p(out), _stream()),
+          "comb_boxes_bev")
+    return out
+
+
+def nms(boxes, thresh, rotated=True, flavour="gpu", trig=None):
+    """boxes (N,7) sorted by descending score. Returns (keep int64 (N,), num_keep int32 (1,)) on device."""
+    lib = _lib.load()
+    _need(boxes, torch.float32, "boxes")
+    _need(trig, torch.float32, "trig")
+    n = int(boxes.shape[0])
+    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=boxes.device)
+    num = torch.empty((1,), dtype=torch.int32, device=boxes.device)
+    ws = _ws(lib.comb_nms_workspace_bytes(n), boxes.device)
+    check(lib.comb_nms(_p(boxes), _p(trig), n, float(thresh), int(bool(rotated)), 0 if flavour == "cpu" else 1,
+                       _p(keep), _p(num), _p(ws), ws.numel(), _stream()), "comb_nms")
+    return keep, num

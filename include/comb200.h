@@ -1,0 +1,223 @@
+/*
+ * comb200.h — C-ABI of libcomb200.so: the B200 (sm_100a) voxel-detector hot path of COM / OpenPCDet.
+ *
+ * Plain pointers + sizes + a CUDA stream in, an int status out.  No torch types.  Every entry point
+ * names the reference interface it replaces (paths relative to the reference tree, `file:line`).
+ *
+ * Conventions
+ *  - All buffer pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ *  - `stream` is a `cudaStream_t` passed as `void*` (0 = legacy default stream).  Nothing here
+ *    synchronises the stream except the functions documented as "blocking".
+ *  - Return value: 0 on success; <0 on error (COMB_E*).  `comb_last_error()` returns a thread-local
+ *    human readable message.  (Reference convention is `fprintf(stderr)+exit(-1)`,
+ *    pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:14-38; status codes are strictly friendlier.)
+ *  - Row counts that are only known on the device are passed as `const int* n_dev` (nullable);
+ *    `n_max` then bounds the launch and threads beyond `*n_dev` exit.  This keeps the whole
+ *    voxelize -> backbone -> BEV chain free of host synchronisation.
+ *  - Coordinates are int32 rows (b, z, y, x) exactly like `voxel_coords` after
+ *    pcdet/datasets/dataset.py:254-259.
+ */
+#ifndef COMB200_H_
+#define COMB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COMB_OK 0
+#define COMB_EINVAL (-1)  /* bad argument */
+#define COMB_ECUDA (-2)   /* CUDA runtime error (message in comb_last_error) */
+#define COMB_ERANGE (-3)  /* a size exceeds what the 32-bit key space supports */
+#define COMB_ENODEV (-4)  /* no sm_100 device */
+
+#define COMB_DT_F32 0
+#define COMB_DT_BF16 1
+
+/* Epilogue flags of the sparse convolution (comb_spconv_fwd_*). */
+#define COMB_EPI_BIAS 1      /* out += bias[co]                      */
+#define COMB_EPI_AFFINE 2    /* out = out*scale[co] + shift[co]  (eval-mode BatchNorm1d folded) */
+#define COMB_EPI_RESIDUAL 4  /* out += residual[o, co]  (SparseBasicBlock identity add)       */
+#define COMB_EPI_RELU 8      /* out = max(out, 0)                    */
+
+/* ---- library ------------------------------------------------------------------------------- */
+int comb_version(void);
+const char* comb_last_error(void);
+/* Number of SMs of the current device (148 on B200); <0 on error. */
+int comb_sm_count(void);
+
+/* ---- a1/a2/a4: voxelization (+ fused MeanVFE) ------------------------------------------------
+ * Replaces spconv.utils.Point2VoxelCPU3d.point_to_voxel / VoxelGenerator.generate as called by
+ * VoxelGeneratorWrapper.generate (pcdet/datasets/processor/data_processor.py:44-60) and, when
+ * `mean_out` is given, MeanVFE.forward (pcdet/models/backbones_3d/vfe/mean_vfe.py:14-31).
+ *
+ * Semantics (bit-exact with the sequential generator): for each frame independently, scanning
+ * points in order: c_j = floor((p_j - range_min_j) / vsize_j) in fp32 (IEEE subtract + divide);
+ * drop the point unless 0 <= c_j < grid_j on all axes; voxel ids are handed out in order of first
+ * appearance, at most `max_voxels` per frame (later new voxels are dropped, their points too);
+ * each voxel keeps its first `max_points` points in point order.
+ *
+ * points       [n_total, C] fp32, frames concatenated.
+ * frame_offsets_host [batch+1] host ints, frame b = rows [off[b], off[b+1]).
+ * voxels       [batch*max_voxels, max_points, C] fp32 or NULL (rows [0,total) written, zero padded)
+ * coords       [batch*max_voxels, 4] int32 (b, z, y, x); frames are packed back to back
+ * num_points   [batch*max_voxels] int32
+ * mean_out     NULL or [batch*max_voxels, mean_ld] (dtype mean_dtype): mean over the kept points of
+ *              channels [mean_c0, C); columns beyond C-mean_c0 up to mean_ld are zero filled
+ * counts       [batch+1] int32 device: voxels per frame, then the total.
+ * workspace    comb_voxelize_workspace_bytes(...) bytes, 256-byte aligned.
+ */
+size_t comb_voxelize_workspace_bytes(int n_total, int batch, int max_voxels, int max_points);
+int comb_voxelize(const float* points, const int* frame_offsets_host, int batch, int C,
+                  const float* vsize_xyz_host, const float* range_xyz_host,
+                  int max_points, int max_voxels,
+                  float* voxels, int* coords, int* num_points,
+                  void* mean_out, int mean_dtype, int mean_c0, int mean_ld,
+                  int* counts, void* workspace, size_t workspace_bytes, void* stream);
+
+/* a4 stand-alone: MeanVFE over an existing (M, T, C) voxel tensor (mean_vfe.py:26-29).
+ * num_points may be int32 (num_is_float=0) or fp32 (=1, as after load_data_to_gpu). */
+int comb_mean_vfe(const float* voxels, const void* num_points, int num_is_float, int M, int T, int C,
+                  float* out, void* stream);
+
+/* ---- a6: coordinate hash table + rulebook ----------------------------------------------------
+ * Replaces the indice-pair generation inside spconv's SubMConv3d / SparseConv3d forward
+ * (call sites pcdet/models/backbones_3d/spconv_backbone.py:191-232).
+ *
+ * The hash table maps linear key ((b*D+z)*H+y)*W+x -> row.  `slots` must be a power of two
+ * >= 2*n_max (comb_hash_slots).  table = slots * 8 bytes (uint32 key, int32 row interleaved).
+ */
+int comb_hash_slots(int n_max);
+int comb_hash_build(const int* coords, int n_max, const int* n_dev, int batch, int D, int H, int W,
+                    void* table, int slots, void* stream);
+
+/* Output coordinate set of a strided SparseConv3d, in canonical order (ascending linear key of
+ * the OUTPUT grid).  out = floor((in + 2p - d(k-1) - 1)/s) + 1 per axis is computed by the caller
+ * and passed as oD,oH,oW.  bitmap workspace: comb_outcoords_workspace_bytes(batch,oD,oH,oW).
+ * out_coords [out_cap,4]; out_count (device int) receives the number of rows (clamped to out_cap).
+ */
+size_t comb_outcoords_workspace_bytes(int batch, int oD, int oH, int oW);
+int comb_conv_out_coords(const int* in_coords, int n_max, const int* n_dev, int batch,
+                         int oD, int oH, int oW,
+                         const int* ksize, const int* stride, const int* pad, const int* dil,
+                         int* out_coords, int out_cap, int* out_count,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gather-form rulebook: nbr[k*ld + o] = input row feeding output row o through kernel offset
+ * k = (kz*KH + ky)*KW + kx, i.e. the row whose coordinate is o*s - p + k*d, or -1.
+ * For SubMConv3d pass out_coords == in_coords, stride 1, pad = k/2 (spconv ignores the user's
+ * padding for SubM).  The classic pair lists are P_k = {(nbr[k][o], o) : nbr[k][o] >= 0}. */
+int comb_nbrmap_build(const int* out_coords, int no_max, const int* no_dev,
+                      const void* in_table, int in_slots, int batch, int iD, int iH, int iW,
+                      const int* ksize, const int* stride, const int* pad, const int* dil,
+                      int* nbr, int ld, void* stream);
+
+/* Scatter-form (transposed) rulebook used by dgrad and SparseInverseConv3d:
+ * nbr_t[k*ld_t + i] = output row o with nbr[k][o] == i, or -1.  */
+int comb_nbrmap_transpose(const int* nbr, int K, int no_max, const int* no_dev, int ld,
+                          int* nbr_t, int ni_max, int ld_t, void* stream);
+
+/* Compact pair lists in spconv's `indice_pairs` layout: pairs[(0*K+k)*ld + j] = in row,
+ * pairs[(1*K+k)*ld + j] = out row for j < pair_num[k], ordered by ascending out row; rest -1. */
+int comb_nbrmap_to_pairs(const int* nbr, int K, int no_max, const int* no_dev, int ld,
+                         int* pairs, int* pair_num, void* stream);
+
+/* ---- a7/a8/a9: sparse convolution ------------------------------------------------------------
+ * Replaces the gather-GEMM-scatter of spconv's SparseConvolution.forward/backward.
+ * Weights are in spconv-2.x layout [Cout, K, Cin] (= (Cout,kz,ky,kx,Cin), one of the layouts
+ * pcdet/models/detectors/detector3d_template.py:337-348 adapts checkpoints to).
+ *
+ *   out[o,:] = epi( sum_k  in[nbr[k][o], :] . W[:,k,:]^T )
+ *
+ * fp32 check mode (CUDA cores, fixed summation order k then ci). */
+int comb_spconv_fwd_f32(const float* in_feats, int Cin, const float* weight, int K, int Cout,
+                        const int* nbr, int ld, int no_max, const int* no_dev,
+                        int epi_flags, const float* bias, const float* scale, const float* shift,
+                        const float* residual, float* out, void* stream);
+/* dgrad: din[i,:] = sum_k dout[nbr_t[k][i], :] . W[:,k,:]   (same kernel family, W not transposed) */
+int comb_spconv_dgrad_f32(const float* dout, int Cout, const float* weight, int K, int Cin,
+                          const int* nbr_t, int ld_t, int ni_max, const int* ni_dev,
+                          float* din, void* stream);
+/* wgrad: dW[co,k,ci] = sum_o dout[o,co] * in[nbr[k][o], ci];  dW is overwritten. */
+int comb_spconv_wgrad_f32(const float* in_feats, int Cin, const float* dout, int Cout, int K,
+                          const int* nbr, int ld, int no_max, const int* no_dev,
+                          float* dweight, void* stream);
+
+/* bf16 tensor-core path: tcgen05.mma (M=128 rows x N=Cout, K chunks of 64 = packed kernel
+ * offsets), fp32 accumulators in TMEM, gathered A rows staged with cp.async into 128B-swizzled
+ * shared memory, packed weights streamed with cp.async.bulk.
+ *  in_feats  [ni, Cin_p] bf16 (Cin_p = Cin rounded up to 16, zero padded)
+ *  wpacked   image produced by comb_spconv_pack_weight_bf16 (bytes: comb_spconv_packed_bytes)
+ *  out       [no, Cout] bf16 (out_dtype=COMB_DT_BF16) or fp32
+ *  residual  [no, Cout] bf16 or NULL
+ * Supported: Cin_p, Cout in {16, 32, 64, 128}. */
+size_t comb_spconv_packed_bytes(int Cin_p, int K, int Cout);
+int comb_spconv_pack_weight_bf16(const float* weight, int Cout, int K, int Cin, int Cin_p,
+                                 void* wpacked, void* stream);
+int comb_spconv_fwd_bf16(const void* in_feats, int Cin_p, const void* wpacked, int K, int Cout,
+                         const int* nbr, int ld, int no_max, const int* no_dev,
+                         int epi_flags, const float* bias, const float* scale, const float* shift,
+                         const void* residual, void* out, int out_dtype, void* stream);
+
+/* Elementwise helpers used between convolutions (a9: BatchNorm1d(eval) + ReLU + residual). */
+int comb_affine_relu(const void* x, int dtype, int n_max, const int* n_dev, int C,
+                     const float* scale, const float* shift, const void* residual, int relu,
+                     void* out, void* stream);
+int comb_cast_pad(const float* x, int n_max, const int* n_dev, int C, void* out_bf16, int ld,
+                  void* stream);
+
+/* ---- a10: HeightCompression / SparseConvTensor.dense() ---------------------------------------
+ * Replaces encoded_spconv_tensor.dense() (pcdet/models/backbones_2d/map_to_bev/
+ * height_compression.py:21): out[b, c, z, y, x] = feats[row, c], zero elsewhere; out is fp32
+ * NCDHW so that .view(N, C*D, H, W) is free.  The whole tensor is written (no prior memset). */
+int comb_dense(const void* feats, int dtype, const int* coords, int n_max, const int* n_dev,
+               int batch, int C, int D, int H, int W, float* out, void* workspace,
+               size_t workspace_bytes, void* stream);
+size_t comb_dense_workspace_bytes(int batch, int D, int H, int W);
+
+/* ---- a11/a12: points in boxes -----------------------------------------------------------------
+ * comb_points_in_boxes_mask replaces points_in_boxes_cpu (pcdet/ops/roiaware_pool3d/src/
+ * roiaware_pool3d.cpp:143-168, MARGIN 1e-2): mask[b*P + p] = 1 iff point p lies in box b.
+ * To be bit-identical with the reference's glibc cosf/sinf the per-box rotation is supplied by
+ * the caller: box_trig [nb,2] = (cosf(-rz), sinf(-rz)) computed with the host libm
+ * (comb_box_trig_host does exactly that).  Arithmetic is IEEE fp32 without FMA contraction and
+ * fp64 thresholds, like the reference compiled by g++ for x86-64.
+ *
+ * comb_points_in_boxes_index replaces points_in_boxes_gpu (roiaware_pool3d_kernel.cu:313-336,
+ * MARGIN 1e-5): idx[b*P+p] = first box of frame b containing the point, or -1; trigonometry and
+ * contraction follow the reference's device code. */
+void comb_box_trig_host(const float* boxes_host, int nb, float* trig_host);
+int comb_points_in_boxes_mask(const float* points, int P, int point_stride, const float* boxes,
+                              const float* box_trig, int nb, int* mask, void* stream);
+int comb_points_in_boxes_index(const float* points, const float* boxes, int batch, int P, int T,
+                               int* idx, void* stream);
+
+/* ---- a13/a14: rotated BEV IoU -----------------------------------------------------------------
+ * flavour 0 ("cpu"): replaces boxes_iou_bev_cpu (pcdet/ops/iou3d_nms/src/iou3d_cpu.cpp:232-252);
+ *   trig_a/trig_b [n,4] = (cosf(rz), sinf(rz), cosf(-rz), sinf(-rz)) from the host libm
+ *   (comb_box_trig4_host), no FMA contraction.
+ * flavour 1 ("gpu"): replaces boxes_iou_bev_gpu / boxes_overlap_bev_gpu (iou3d_nms.cpp:49-88,
+ *   kernels iou3d_nms_kernel.cu:236-265); trig pointers may be NULL (computed on device).
+ * what: 0 = IoU, 1 = overlap area. out [na, nb] fp32. */
+void comb_box_trig4_host(const float* boxes_host, int n, float* trig_host);
+int comb_boxes_bev(const float* boxes_a, const float* trig_a, int na,
+                   const float* boxes_b, const float* trig_b, int nb,
+                   int flavour, int what, float* out, void* stream);
+
+/* ---- a15/a16: NMS ------------------------------------------------------------------------------
+ * Replaces nms_gpu / nms_normal_gpu (iou3d_nms.cpp:90-188 + kernels :267-372): boxes must already
+ * be sorted by descending score (the Python wrapper does that, iou3d_nms_utils.py:91-95).
+ * The suppression bit-matrix and the greedy sweep both run on the device; `keep` [n] int64 and
+ * `num_keep` (1 int) are device buffers.  rotated=1 -> rotated BEV IoU, 0 -> axis aligned.
+ * flavour as in comb_boxes_bev (trig may be NULL for flavour 1).
+ * workspace: comb_nms_workspace_bytes(n). */
+size_t comb_nms_workspace_bytes(int n);
+int comb_nms(const float* boxes, const float* trig, int n, float thresh, int rotated, int flavour,
+             long long* keep, int* num_keep, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMB200_H_ */
