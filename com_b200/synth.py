@@ -103,10 +103,11 @@ def make_boxes(n, seed=0, rng_xy=75.2):
     return np.concatenate([xy, z, d, h], axis=1).astype(np.float32)
 
 
-def make_clustered_boxes(n, seed=0, spread=6.0, centers=40):
-    """Boxes bunched around a few centres so that many pairs overlap (NMS / IoU stress)."""
+def make_clustered_boxes(n, seed=0, spread=6.0, centers=40, center_seed=12345):
+    """Boxes bunched around a few centres so that many pairs overlap (NMS / IoU stress).
+    The centres depend on `center_seed` only, so sets drawn with different seeds overlap each other."""
     rng = np.random.default_rng(seed)
-    ctr = rng.uniform(-60, 60, size=(centers, 2))
+    ctr = np.random.default_rng(center_seed).uniform(-60, 60, size=(centers, 2))
     xy = ctr[rng.integers(0, centers, size=n)] + rng.normal(0, spread / 3, size=(n, 2))
     z = rng.uniform(-1.0, 1.0, size=(n, 1))
     d = np.stack([rng.uniform(3.5, 5.5, n), rng.uniform(1.6, 2.2, n), rng.uniform(1.4, 2.0, n)], axis=1)

@@ -1,0 +1,56 @@
+"""N>1 host path on CPU: world_size-2 gloo processes shard frames with no data-path collective and
+reduce timings with max / counters with sum (bench.py's multi-GPU contract)."""
+import os
+import socket
+
+import torch.multiprocessing as mp
+
+from com_b200 import dist as cdist
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    r, lr, w = cdist.init(backend="gloo")
+    mine = cdist.frame_shard(7, r, w)
+    cdist.barrier()
+    t = cdist.max_over_ranks(10.0 + r, device="cpu")
+    n = cdist.sum_over_ranks(len(mine), device="cpu")
+    q.put((r, mine, t, n))
+    import torch.distributed as dist
+    dist.destroy_process_group()
+
+
+def test_frame_shard_partition():
+    for world in (1, 2, 3, 8):
+        got = sorted(sum((cdist.frame_shard(13, r, world) for r in range(world)), []))
+        assert got == list(range(13))
+    assert cdist.frame_shard(0, 0, 2) == [] and cdist.frame_shard(1, 1, 2) == []
+
+
+def test_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][1] == [0, 2, 4, 6] and res[1][1] == [1, 3, 5]
+    assert res[0][2] == res[1][2] == 11.0           # max over ranks
+    assert res[0][3] == res[1][3] == 7.0            # every frame processed exactly once
+
+
+def test_single_process_is_a_noop():
+    assert cdist.max_over_ranks(3.5) == 3.5 and cdist.sum_over_ranks(2) == 2
