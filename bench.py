@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the COM voxel-detector hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the hot path over one batch of synthetic Waymo-shaped frames:
+voxelize (+MeanVFE) -> VoxelResBackBone8x forward (21 sparse convs, eval BN/ReLU/residual fused) ->
+HeightCompression, on the 1504x1504x40 grid, batch 4 per GPU (BASELINE configs[1]).  N>1 (torchrun):
+every rank runs its own batch of 4 frames (frames are independent units: weak scaling, no data-path
+collective); times are max over ranks.
+
+Prints ONE JSON line.  `value` = device-resident throughput (CUDA events, L2 flushed between steps);
+`e2e` = the same through FramePipeline.forward_host with pinned host buffers, H2D and D2H inside the
+timed region; `roofline` = the dominant kernel (tcgen05 gather-GEMM) timed with CUDA events inside the
+timed steps; `cpu_baseline` = the CPU restatement (oracle/, OpenMP) on the host cores, bounded sample.
+`--impl reference` times that CPU implementation alone (spconv is not vendored by the reference, so the
+"reference CPU path" is the restatement of its semantics).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frames/s voxelize+VoxelResBackBone8x fwd, Waymo shape"
+UNIT = "frames/s"
+BATCH = 4
+WORKLOAD = "configs[1]: CenterPoint-Voxel VoxelResBackBone8x forward (1504x1504x40 grid), batch 4 per GPU, " \
+           "synthetic ~180k-point x 5-feature frames, voxelize+MeanVFE+backbone+HeightCompression"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
+                    tf_sust=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def make_frames(seeds):
+    from com_b200 import synth
+    cache = os.path.join("/tmp", "comb200_frames")
+    os.makedirs(cache, exist_ok=True)
+    out = []
+    for s in seeds:
+        f = os.path.join(cache, "frame_%d.npy" % s)
+        if os.path.exists(f):
+            out.append(np.load(f))
+        else:
+            a = synth.make_frame(seed=s)
+            try:
+                np.save(f, a)
+            except OSError:
+                pass
+            out.append(a)
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                p = [x.strip() for x in o.strip().split(",")]
+                if len(p) >= 6:
+                    self.rows.append(p)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+class EventProfiler:
+    """ops profiler hook: CUDA events around every kernel family on the launching (current) stream."""
+
+    def __init__(self, torch, analyse=False):
+        self.torch, self.analyse = torch, analyse
+        self.records, self._open = [], None
+
+    def begin(self, tag, **info):
+        e0 = self.torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self._open = (tag, info, e0)
+
+    def end(self):
+        tag, info, e0 = self._open
+        e1 = self.torch.cuda.Event(enable_timing=True)
+        e1.record()
+        meta = None
+        if self.analyse:
+            meta = self._meta(tag, info)
+        self.records.append((tag, e0, e1, meta))
+
+    def _meta(self, tag, info):
+        t = self.torch
+        if tag == "spconv_fwd_bf16":
+            n = int(info["no_dev"].item()) if info["no_dev"] is not None else info["no"]
+            n = min(n, info["no"])
+            pairs = int((info["nbr"][:, :n] >= 0).sum().item())
+            return dict(cin=info["cin"], cout=info["cout"], K=info["K"], no=n, ni=info["ni"], pairs=pairs,
+                        residual=bool(info["residual"]), out_bytes=info["out_bytes"])
+        if tag == "voxelize":
+            c = info["counts"].tolist()
+            return dict(n=info["n"], C=info["C"], T=info["T"], M=c[-1], mean_ld=info["mean_ld"],
+                        mean_bytes=info["mean_bytes"], want_voxels=bool(info["want_voxels"]))
+        if tag == "dense":
+            return dict(n=info["n"], C=info["C"], cells=info["cells"], in_bytes=info["in_bytes"])
+        if tag == "nbrmap_build":
+            n = int(info["no_dev"].item()) if info["no_dev"] is not None else info["no"]
+            return dict(no=min(n, info["no"]), K=info["K"])
+        if tag == "hash_build":
+            n = int(info["n_dev"].item()) if info["n_dev"] is not None else info["n"]
+            return dict(n=min(n, info["n"]), slots=info["slots"])
+        if tag == "conv_out_coords":
+            n = int(info["n_dev"].item()) if info["n_dev"] is not None else info["n"]
+            return dict(n=min(n, info["n"]), no=int(info["out_count"].item()), bitmap_bytes=info["bitmap_bytes"])
+        return {}
+
+    def times_ms(self):
+        return [(tag, e0.elapsed_time(e1), meta) for tag, e0, e1, meta in self.records]
+
+
+def algorithmic(tag, m):
+    """(bytes, flops) per launch family — SURVEY.md §8(d) formulas (DESIGN.md restates them)."""
+    if tag == "spconv_fwd_bf16":
+        flops = 2.0 * m["pairs"] * m["cin"] * m["cout"]
+        by = (m["ni"] * m["cin"] + m["no"] * m["cout"] * (2 if m["residual"] else 1)) * 2.0 \
+            + m["K"] * m["cin"] * m["cout"] * 2.0
+        if m["out_bytes"] == 4:
+            by += m["no"] * m["cout"] * 2.0
+        return by, flops
+    if tag == "voxelize":
+        by = m["n"] * m["C"] * 4.0 + m["M"] * 16.0 + m["M"] * 4.0 + m["M"] * m["mean_ld"] * m["mean_bytes"]
+        if m["want_voxels"]:
+            by += m["M"] * m["T"] * m["C"] * 4.0
+        return by, 0.0
+    if tag == "dense":
+        return m["cells"] * m["C"] * 4.0 + m["n"] * m["C"] * m["in_bytes"] + m["n"] * 16.0, 0.0
+    if tag == "nbrmap_build":
+        return m["no"] * 16.0 + m["no"] * m["K"] * 4.0, 0.0
+    if tag == "hash_build":
+        return m["n"] * 16.0 + m["n"] * 8.0, 0.0
+    if tag == "conv_out_coords":
+        return m["n"] * 16.0 + m["no"] * 16.0, 0.0
+    return 0.0, 0.0
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_run_frames(frames, sd, threads=None):
+    """One pass of the hot path on the host cores (oracle/, OpenMP fp32 conv). Returns seconds."""
+    import oracle
+    from com_b200 import synth
+    from oracle import cpu_pipeline
+    if threads:
+        oracle.fast().orc_fast_set_threads(int(threads))
+    t0 = time.perf_counter()
+    cpu_pipeline.frame_forward(frames, sd, synth.VOXEL_SIZE, synth.POINT_CLOUD_RANGE, synth.MAX_POINTS_PER_VOXEL,
+                               synth.MAX_NUMBER_OF_VOXELS, conv=oracle.fast_conv_fwd, want_dense=True)
+    return time.perf_counter() - t0
+
+
+def cpu_state_dict():
+    import torch
+    from com_b200 import models
+    torch.manual_seed(0)
+    m = models.VoxelResBackBone8x(None, 5, [1504, 1504, 40]).eval()
+    return {k: v.detach() for k, v in m.state_dict().items()}
+
+
+def reference_arm(args):
+    """--impl reference: the CPU implementation of the path on the box's host cores (all threads),
+    each step = a bounded sample (1 frame) of the workload."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    cores = oracle.fast().orc_fast_threads()
+    frames = make_frames([1000])
+    sd = cpu_state_dict()
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_run_frames(frames, sd)
+    steps = max(1, min(args.steps, 5))
+    t = sum(cpu_run_frames(frames, sd) for _ in range(steps))
+    val = steps * len(frames) / t
+    sample = "1 frame (of the %d-frame batch) per step, %d steps; voxelize+MeanVFE+backbone+dense on CPU" % (BATCH, steps)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def ours(args):
+    import torch
+    from com_b200 import _lib, dist as cdist, ops, pipeline
+    rank, local_rank, world = cdist.init()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load(build_if_missing=False)
+    peaks = load_peaks()
+
+    frames = make_frames([1000 + rank * BATCH + b for b in range(BATCH)])
+    offs = np.concatenate([[0], np.cumsum([len(f) for f in frames])]).astype(int).tolist()
+    host = torch.from_numpy(np.concatenate(frames, axis=0)).pin_memory()
+    pts = host.to(dev)
+    pipe = pipeline.FramePipeline(device=dev, seed=0)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        return pipe.forward_device(pts, offs)
+
+    def step_e2e(out_host):
+        bd = pipe.forward_host(None, pinned=(host, offs))
+        enc = bd["encoded_spconv_tensor"]
+        n = enc.features.shape[0]
+        out_host["feat"][:n].copy_(enc.features, non_blocking=True)
+        out_host["idx"][:n].copy_(enc.indices, non_blocking=True)
+        out_host["cnt"].copy_(bd["voxel_counts"], non_blocking=True)
+        return n, bd
+
+    for _ in range(max(args.warmup, 3)):
+        bd = step_device()
+    torch.cuda.synchronize()
+    enc_rows = int(bd["encoded_spconv_tensor"].features.shape[0])
+    n_vox = int(bd["voxel_coords"].shape[0])
+
+    # analysis pass (untimed): per-launch algorithmic bytes / flops from the actual rulebooks
+    prof = EventProfiler(torch, analyse=True)
+    ops.set_profiler(prof)
+    step_device()
+    torch.cuda.synchronize()
+    metas = [(tag, meta) for tag, _, meta in prof.times_ms()]
+    ops.set_profiler(None)
+
+    # ---- timed region: K steps, device-resident inputs, L2 flushed between steps -------------------
+    sampler = ClockSampler(local_rank)
+    cdist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = lib.comb_launch_count()
+    prof = EventProfiler(torch)
+    ops.set_profiler(prof)
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)                      # evict the 126 MB L2 (outside the timed window)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_device()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    cdist.barrier()
+    ops.set_profiler(None)
+    launches = (lib.comb_launch_count() - launches0) // max(args.steps, 1)
+    t_dev = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+    fam = {}
+    per_step = len(prof.records) // max(args.steps, 1)
+    for i, (tag, ms, _) in enumerate(prof.times_ms()):
+        meta = metas[i % per_step][1]
+        by, fl = algorithmic(tag, meta)
+        f = fam.setdefault(tag, dict(ms=0.0, bytes=0.0, flops=0.0, launches=0))
+        f["ms"] += ms
+        f["bytes"] += by
+        f["flops"] += fl
+        f["launches"] += 1
+    conv_layers = {}
+    for i, (tag, ms, _) in enumerate(prof.times_ms()):
+        if tag != "spconv_fwd_bf16":
+            continue
+        meta = metas[i % per_step][1]
+        key = "%dx%d_K%d" % (meta["cin"], meta["cout"], meta["K"])
+        c = conv_layers.setdefault(key, dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
+        by, fl = algorithmic(tag, meta)
+        c["ms"] += ms
+        c["flops"] += fl
+        c["bytes"] += by
+        c["n"] += 1
+
+    # ---- e2e: public API, pinned host input -> device -> compact result back to pinned host --------
+    out_host = {"feat": torch.empty((max(enc_rows * 2, 1024), 128), dtype=torch.bfloat16).pin_memory(),
+                "idx": torch.empty((max(enc_rows * 2, 1024), 4), dtype=torch.int32).pin_memory(),
+                "cnt": torch.empty((BATCH + 1,), dtype=torch.int32).pin_memory()}
+    for _ in range(2):
+        step_e2e(out_host)
+    torch.cuda.synchronize()
+    cdist.barrier()
+    e2e_evs, d2h = [], 0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n, _ = step_e2e(out_host)
+        e1.record()
+        e1.synchronize()                    # the caller owns the result only after the D2H has landed
+        e2e_evs.append((e0, e1))
+        d2h = n * 128 * 2 + n * 16 + (BATCH + 1) * 4
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    cdist.barrier()
+    clocks = sampler.stop()
+    t_e2e = sum(a.elapsed_time(b) for a, b in e2e_evs) / 1e3
+
+    t_dev_max = cdist.max_over_ranks(t_dev)
+    t_e2e_max = cdist.max_over_ranks(t_e2e)
+    total_frames = world * BATCH * args.steps
+
+    line = None
+    if rank == 0:
+        conv = fam.get("spconv_fwd_bf16", dict(ms=1e-9, flops=0, bytes=0, launches=1))
+        conv_s = conv["ms"] / 1e3
+        tf = conv["flops"] / conv_s / 1e12
+        roof = {"bound": "tensor", "kernel": "spconv_tc_kernel (tcgen05 gather-GEMM, 21 launches/step)",
+                "achieved": tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": tf / peaks["tf_sust"],
+                "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks["src"],
+                "traffic": None,
+                "share_of_step": conv_s / t_dev,
+                "hbm_view": {"achieved": conv["bytes"] / conv_s / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                             "frac": conv["bytes"] / conv_s / 1e9 / peaks["hbm"]},
+                "layers": {k: {"ms_per_launch": v["ms"] / v["n"], "tflops": v["flops"] / (v["ms"] / 1e3) / 1e12,
+                               "gbs": v["bytes"] / (v["ms"] / 1e3) / 1e9} for k, v in conv_layers.items()}}
+        hbm_kernels = {}
+        for tag in ("voxelize", "dense", "nbrmap_build", "hash_build", "conv_out_coords"):
+            if tag in fam and fam[tag]["ms"] > 0:
+                f = fam[tag]
+                g = f["bytes"] / (f["ms"] / 1e3) / 1e9
+                hbm_kernels[tag] = {"ms_per_step": f["ms"] / args.steps, "achieved": g, "unit": "GB/s",
+                                    "frac": g / peaks["hbm"], "share_of_step": f["ms"] / 1e3 / t_dev}
+        roof["hbm_kernels"] = hbm_kernels
+
+        # CPU baseline on a bounded sample (rank 0, N=1 only): 1 frame of the batch
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            import oracle
+            oracle.build()
+            sd = {k: v.detach().cpu() for k, v in pipe.backbone.state_dict().items()}
+            cores = oracle.fast().orc_fast_threads()
+            cpu_run_frames(frames[:1], sd)
+            reps = 2
+            tc = sum(cpu_run_frames(frames[:1], sd) for _ in range(reps))
+            cpu = {"value": reps / tc, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "1 of the 4 frames x %d passes: voxelize+MeanVFE+backbone+dense, OpenMP fp32 "
+                             "restatement of the spconv CPU semantics (oracle/cpu_fast.c)" % reps}
+        line = {
+            "metric": METRIC, "value": total_frames / t_dev_max, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu": BATCH, "points_per_frame": [int(len(f)) for f in frames],
+                       "voxels_per_batch": n_vox, "encoded_rows": enc_rows, "parallelism": "frames x%d" % world,
+                       "l2": "flushed between steps (512 MiB write outside the timed window)"},
+            "e2e": {"value": total_frames / t_e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e_max / args.steps,
+                    "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+                    "result": "encoded_spconv_tensor (features bf16 + indices) + voxel counts to pinned host; "
+                              "the dense BEV tensor is produced on the device"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "breakdown_ms_per_step": {k: v["ms"] / args.steps for k, v in fam.items()},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    cdist.barrier()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,7 @@ SIGNATURES = {
     "comb_version": (c_int, []),
     "comb_last_error": (c_char_p, []),
     "comb_sm_count": (c_int, []),
+    "comb_launch_count": (c_longlong, []),
     "comb_voxelize_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "comb_voxelize": (c_int, [_P, _PI, c_int, c_int, _PF, _PF, c_int, c_int, _P, _P, _P, _P, c_int, c_int, c_int,
                               _P, _P, c_size_t, _P]),

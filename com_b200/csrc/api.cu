@@ -1,11 +1,15 @@
 // Library-level entry points and error plumbing of libcomb200.
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace comb {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -38,6 +42,8 @@ int sm_count() {
 extern "C" {
 
 int comb_version(void) { return 100; }
+
+long long comb_launch_count(void) { return comb::g_launches.load(std::memory_order_relaxed); }
 
 const char* comb_last_error(void) { return comb::g_err; }
 

@@ -14,6 +14,7 @@ namespace comb {
 
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+void count_launch();
 
 #define COMB_CHECK_ARG(cond, ...)      \
   do {                                 \
@@ -29,7 +30,13 @@ int check_cuda(cudaError_t e, const char* what);
     if (_rc != COMB_OK) return _rc;                      \
   } while (0)
 
-#define COMB_LAUNCH_CHECK(name) COMB_CUDA(cudaPeekAtLastError())
+// every kernel launch of the library is followed by exactly one COMB_LAUNCH_CHECK: it also feeds the
+// launch counter behind comb_launch_count() (bench.py's "gpu_launches").
+#define COMB_LAUNCH_CHECK(name)           \
+  do {                                    \
+    comb::count_launch();                 \
+    COMB_CUDA(cudaPeekAtLastError());     \
+  } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -364,7 +364,8 @@ extern "C" int comb_nbrmap_build(const int* out_coords, int no_max, const int* n
                                  int in_slots, int batch, int iD, int iH, int iW, const int* ksize, const int* stride,
                                  const int* pad, const int* dil, int* nbr, int ld, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  COMB_CHECK_ARG(ksize && in_table && nbr && ld >= no_max && no_max >= 0, "comb_nbrmap_build: bad arguments");
+  COMB_CHECK_ARG(ksize && ld >= no_max && no_max >= 0, "comb_nbrmap_build: bad arguments");
+  COMB_CHECK_ARG(no_max == 0 || (in_table && nbr), "comb_nbrmap_build: null table/nbr pointer");
   COMB_CHECK_ARG(in_slots > 0 && (in_slots & (in_slots - 1)) == 0, "comb_nbrmap_build: slots must be a power of two");
   Conv3 cv;
   COMB_CHECK_ARG(fill_conv3(cv, ksize, stride, pad, dil) == 0, "comb_nbrmap_build: bad conv parameters");
@@ -382,7 +383,10 @@ extern "C" int comb_nbrmap_build(const int* out_coords, int no_max, const int* n
 extern "C" int comb_nbrmap_transpose(const int* nbr, int K, int no_max, const int* no_dev, int ld, int* nbr_t,
                                      int ni_max, int ld_t, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  COMB_CHECK_ARG(nbr_t && K >= 1 && ld_t >= ni_max && ld >= no_max, "comb_nbrmap_transpose: bad arguments");
+  COMB_CHECK_ARG(K >= 1 && ld_t >= ni_max && ni_max >= 0 && ld >= no_max && no_max >= 0,
+                 "comb_nbrmap_transpose: bad arguments");
+  if (ld_t == 0) return COMB_OK;
+  COMB_CHECK_ARG(nbr_t, "comb_nbrmap_transpose: null nbr_t");
   COMB_CUDA(cudaMemsetAsync(nbr_t, 0xFF, (size_t)K * ld_t * 4, stream));
   if (no_max == 0 || ni_max == 0) return COMB_OK;
   COMB_CHECK_ARG(nbr, "comb_nbrmap_transpose: null nbr");
@@ -397,7 +401,8 @@ extern "C" int comb_nbrmap_transpose(const int* nbr, int K, int no_max, const in
 extern "C" int comb_nbrmap_to_pairs(const int* nbr, int K, int no_max, const int* no_dev, int ld, int* pairs,
                                     int* pair_num, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  COMB_CHECK_ARG(nbr && pairs && pair_num && K >= 1 && ld >= no_max, "comb_nbrmap_to_pairs: bad arguments");
+  COMB_CHECK_ARG(pair_num && K >= 1 && ld >= no_max && no_max >= 0, "comb_nbrmap_to_pairs: bad arguments");
+  COMB_CHECK_ARG(ld == 0 || (nbr && pairs), "comb_nbrmap_to_pairs: null nbr/pairs pointer");
   nbr_pairs_kernel<<<K, 1024, 0, stream>>>(nbr, K, no_max, no_dev, ld, pairs, pair_num);
   COMB_LAUNCH_CHECK();
   return COMB_OK;

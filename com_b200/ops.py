@@ -24,6 +24,33 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+# Optional profiler hook (bench.py): an object with begin(tag, **info) / end() called around each
+# kernel family on the launching stream.  None in production.
+_prof = None
+
+
+def set_profiler(p):
+    global _prof
+    _prof = p
+
+
+class _Scope:
+    __slots__ = ("on",)
+
+    def __init__(self, tag, **info):
+        self.on = _prof is not None
+        if self.on:
+            _prof.begin(tag, **info)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            _prof.end()
+        return False
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -82,9 +109,11 @@ def voxelize(points, frame_offsets, vsize_xyz, range_xyz, max_points, max_voxels
     offs = (ctypes.c_int * (batch + 1))(*[int(x) for x in frame_offsets])
     vs = (ctypes.c_float * 3)(*[float(np.float32(x)) for x in vsize_xyz])
     rg = (ctypes.c_float * 6)(*[float(np.float32(x)) for x in range_xyz])
-    check(lib.comb_voxelize(_p(points), offs, batch, C, vs, rg, int(max_points), int(max_voxels), _p(voxels),
-                            _p(coords), _p(num), _p(mean), mdt, int(mean_c0), int(mean_ld or 1), _p(counts), _p(ws),
-                            ws.numel(), _stream()), "comb_voxelize")
+    with _Scope("voxelize", n=n_total, C=C, T=int(max_points), counts=counts, batch=batch,
+                want_voxels=want_voxels, mean_ld=int(mean_ld or 0), mean_bytes=(mean.element_size() if mean is not None else 0)):
+        check(lib.comb_voxelize(_p(points), offs, batch, C, vs, rg, int(max_points), int(max_voxels), _p(voxels),
+                                _p(coords), _p(num), _p(mean), mdt, int(mean_c0), int(mean_ld or 1), _p(counts), _p(ws),
+                                ws.numel(), _stream()), "comb_voxelize")
     return dict(voxels=voxels, coords=coords, num_points=num, counts=counts, mean=mean)
 
 
@@ -114,8 +143,9 @@ def hash_build(coords, batch, shape, n_dev=None):
     slots = lib.comb_hash_slots(n)
     table = torch.empty((slots * 8,), dtype=torch.uint8, device=coords.device)
     D, H, W = [int(x) for x in shape]
-    check(lib.comb_hash_build(_p(coords), n, _p(n_dev), int(batch), D, H, W, _p(table), slots, _stream()),
-          "comb_hash_build")
+    with _Scope("hash_build", n=n, n_dev=n_dev, slots=slots):
+        check(lib.comb_hash_build(_p(coords), n, _p(n_dev), int(batch), D, H, W, _p(table), slots, _stream()),
+              "comb_hash_build")
     return table, slots
 
 
@@ -134,9 +164,11 @@ def conv_out_coords(in_coords, batch, out_shape, ksize, stride, pad, dil, out_ca
     ws = _ws(lib.comb_outcoords_workspace_bytes(int(batch), oD, oH, oW), dev)
     out = torch.empty((int(out_cap), 4), dtype=torch.int32, device=dev)
     cnt = torch.empty((1,), dtype=torch.int32, device=dev)
-    check(lib.comb_conv_out_coords(_p(in_coords), int(in_coords.shape[0]), _p(n_dev), int(batch), oD, oH, oW,
-                                   int3(ksize), int3(stride), int3(pad), int3(dil), _p(out), int(out_cap), _p(cnt),
-                                   _p(ws), ws.numel(), _stream()), "comb_conv_out_coords")
+    with _Scope("conv_out_coords", n=int(in_coords.shape[0]), n_dev=n_dev, out_count=cnt,
+                bitmap_bytes=int(batch) * oD * oH * oW // 8):
+        check(lib.comb_conv_out_coords(_p(in_coords), int(in_coords.shape[0]), _p(n_dev), int(batch), oD, oH, oW,
+                                       int3(ksize), int3(stride), int3(pad), int3(dil), _p(out), int(out_cap), _p(cnt),
+                                       _p(ws), ws.numel(), _stream()), "comb_conv_out_coords")
     return out, cnt
 
 
@@ -150,9 +182,10 @@ def nbrmap_build(out_coords, table, slots, batch, in_shape, ksize, stride, pad, 
     K = int(ksize[0]) * int(ksize[1]) * int(ksize[2])
     nbr = torch.empty((K, ld), dtype=torch.int32, device=out_coords.device)
     iD, iH, iW = [int(x) for x in in_shape]
-    check(lib.comb_nbrmap_build(_p(out_coords), no, _p(no_dev), _p(table), int(slots), int(batch), iD, iH, iW,
-                                int3(ksize), int3(stride), int3(pad), int3(dil), _p(nbr), ld, _stream()),
-          "comb_nbrmap_build")
+    with _Scope("nbrmap_build", no=no, no_dev=no_dev, K=K, nbr=nbr):
+        check(lib.comb_nbrmap_build(_p(out_coords), no, _p(no_dev), _p(table), int(slots), int(batch), iD, iH, iW,
+                                    int3(ksize), int3(stride), int3(pad), int3(dil), _p(nbr), ld, _stream()),
+              "comb_nbrmap_build")
     return nbr
 
 
@@ -275,9 +308,11 @@ def spconv_fwd_bf16(feats, wpacked, K, Cout, nbr, bias=None, scale=None, shift=N
     no = ld if no is None else int(no)
     if out is None:
         out = torch.empty((no, Cout), dtype=out_dtype, device=feats.device)
-    check(lib.comb_spconv_fwd_bf16(_p(feats), cin_p, _p(wpacked), int(K), int(Cout), _p(nbr), ld, no, _p(no_dev),
-                                   _epi_flags(bias, scale, shift, residual, relu), _p(bias), _p(scale), _p(shift),
-                                   _p(residual), _p(out), _dt(out), _stream()), "comb_spconv_fwd_bf16")
+    with _Scope("spconv_fwd_bf16", cin=cin_p, cout=int(Cout), K=int(K), nbr=nbr, no=no, no_dev=no_dev,
+                ni=int(feats.shape[0]), residual=residual is not None, out_bytes=out.element_size()):
+        check(lib.comb_spconv_fwd_bf16(_p(feats), cin_p, _p(wpacked), int(K), int(Cout), _p(nbr), ld, no, _p(no_dev),
+                                       _epi_flags(bias, scale, shift, residual, relu), _p(bias), _p(scale), _p(shift),
+                                       _p(residual), _p(out), _dt(out), _stream()), "comb_spconv_fwd_bf16")
     return out
 
 
@@ -309,8 +344,9 @@ def dense(feats, coords, batch, shape, n_dev=None):
     n, C = int(feats.shape[0]), int(feats.shape[1])
     out = torch.empty((int(batch), C, D, H, W), dtype=torch.float32, device=feats.device)
     ws = _ws(lib.comb_dense_workspace_bytes(int(batch), D, H, W), feats.device)
-    check(lib.comb_dense(_p(feats), _dt(feats), _p(coords), n, _p(n_dev), int(batch), C, D, H, W, _p(out), _p(ws),
-                         ws.numel(), _stream()), "comb_dense")
+    with _Scope("dense", n=n, C=C, cells=int(batch) * D * H * W, in_bytes=feats.element_size()):
+        check(lib.comb_dense(_p(feats), _dt(feats), _p(coords), n, _p(n_dev), int(batch), C, D, H, W, _p(out), _p(ws),
+                             ws.numel(), _stream()), "comb_dense")
     return out
 
 

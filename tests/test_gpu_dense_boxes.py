@@ -1,0 +1,141 @@
+"""a10-a16 parity: dense() scatter, points_in_boxes (both semantics), rotated BEV IoU and NMS through
+the C-ABI vs the CPU oracle / golden vectors of the reference / the reference's own CUDA build."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from com_b200 import ops, synth
+from com_b200.pcdet_ops import box_ops
+from oracle import build_ref
+from util import GOLDEN, random_coords
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "box_ops_ref.npz"))
+
+
+@pytest.mark.parametrize("C,dtype", [(128, torch.float32), (128, torch.bfloat16), (5, torch.float32), (33, torch.float32)])
+def test_dense(C, dtype):
+    rng = np.random.default_rng(C)
+    batch, shape = 3, [2, 47, 45]
+    coords = random_coords(rng, 2500, batch, shape)
+    feats = rng.normal(size=(len(coords), C)).astype(np.float32)
+    f = cuda(feats).to(dtype)
+    got = ops.dense(f, cuda(coords), batch, shape).cpu().numpy()
+    want = oracle.dense(f.float().cpu().numpy(), coords, batch, shape)
+    assert got.shape == (batch, C, 2, 47, 45) and np.array_equal(got, want)
+    empty = ops.dense(f[:0], cuda(coords[:0]), batch, shape)
+    assert float(empty.abs().sum()) == 0.0
+
+
+def test_points_in_boxes_cpu_semantics_golden(gold):
+    boxes, pts = gold["pib_boxes"], gold["pib_points"]
+    want = np.unpackbits(gold["pib_mask_packed"], axis=1)[:, : len(pts)].astype(np.int32)
+    got = box_ops.points_in_boxes_cpu(pts, boxes)           # numpy in -> numpy out like the reference wrapper
+    assert isinstance(got, np.ndarray) and got.dtype == np.int32 and np.array_equal(got, want)
+
+
+def test_points_in_boxes_cpu_semantics_waymo_size():
+    pts = synth.make_frame(seed=1002)[:, :3].copy()
+    boxes = synth.make_boxes(500, seed=0)
+    boxes[:, 2] = -1.0
+    want = oracle.points_in_boxes_cpu(pts, boxes)
+    got = box_ops.points_in_boxes_cpu(torch.from_numpy(pts), torch.from_numpy(boxes))
+    assert want.sum() > 1000 and np.array_equal(got.numpy(), want)
+    kept = box_ops.remove_points_in_boxes3d(pts, boxes[:35])
+    assert len(kept) == len(pts) - int((want[:35].sum(0) != 0).sum())
+
+
+def test_bev_iou_cpu_semantics_golden(gold):
+    for name in ("uc", "cc", "self", "known"):
+        got = box_ops.boxes_bev_iou_cpu(gold["iou_%s_a" % name], gold["iou_%s_b" % name])
+        want = gold["iou_%s" % name]
+        bad = int((got.view(np.uint32) != want.view(np.uint32)).sum())
+        assert np.array_equal(got == 0, want == 0), name        # what COMAug consumes (== 0 test) must be exact
+        assert bad == 0, "%s: %d of %d IoU values differ in bits (max abs %.3g)" % (
+            name, bad, want.size, np.abs(got - want).max())
+
+
+def test_bev_iou_cpu_semantics_500x500():
+    a = synth.make_clustered_boxes(500, seed=21)
+    want = oracle.boxes_bev_cpu(a, a)
+    got = box_ops.boxes_bev_iou_cpu(a, a)
+    assert (want > 0).sum() > 2000
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_nms_cpu_flavour_keep_list():
+    boxes = synth.make_clustered_boxes(500, seed=22)
+    for thresh in (0.1, 0.7):
+        want = oracle.nms_cpu(boxes, thresh)
+        trig = cuda(ops.box_trig4_host(boxes))
+        keep, num = ops.nms(cuda(boxes), thresh, rotated=True, flavour="cpu", trig=trig)
+        got = keep[: int(num)].cpu().numpy()
+        assert np.array_equal(got, want) and 0 < len(want) < 500
+
+
+ref_cuda = pytest.mark.skipif(not build_ref.available(), reason="oracle/_ref (reference CUDA build) not present")
+
+
+@ref_cuda
+def test_gpu_flavour_vs_reference_cuda_iou_and_nms():
+    """Device flavour vs the reference's own kernels (iou3d_nms_kernel.cu) compiled for sm_100."""
+    ref = build_ref.load_ref("ref_iou3d_nms_cuda")
+    a, b = cuda(synth.make_clustered_boxes(300, seed=31)), cuda(synth.make_clustered_boxes(400, seed=32))
+    for fn_ref, fn in ((ref.boxes_iou_bev_gpu, box_ops.boxes_iou_bev),):
+        want = torch.zeros((300, 400), device="cuda")
+        fn_ref(a, b, want)
+        got = fn(a, b)
+        assert (want > 0).sum() > 1000
+        assert torch.equal(got, want), "%d IoU values differ" % int((got != want).sum())
+    boxes = cuda(synth.make_clustered_boxes(1000, seed=33))
+    scores = torch.from_numpy(np.random.default_rng(3).uniform(size=1000).astype(np.float32)).cuda()
+    order = scores.sort(0, descending=True)[1]
+    sb = boxes[order].contiguous()
+    for thresh in (0.1, 0.7):
+        keep = torch.zeros(1000, dtype=torch.int64)
+        n = ref.nms_gpu(sb, keep, thresh)
+        want = order[keep[:n].cuda()]
+        got, _ = box_ops.nms_gpu(boxes, scores, thresh)
+        assert torch.equal(got, want)
+        keep = torch.zeros(1000, dtype=torch.int64)
+        n = ref.nms_normal_gpu(sb, keep, thresh)
+        got, _ = box_ops.nms_normal_gpu(boxes, scores, thresh)
+        assert torch.equal(got, order[keep[:n].cuda()])
+
+
+@ref_cuda
+def test_points_in_boxes_gpu_vs_reference_cuda():
+    ref = build_ref.load_ref("ref_roiaware_pool3d_cuda")
+    rng = np.random.default_rng(41)
+    boxes = np.stack([synth.make_boxes(60, seed=s) for s in (1, 2)])
+    pts = (boxes[:, rng.integers(0, 60, 30000), :3] + rng.normal(0, 1.5, size=(2, 30000, 3))).astype(np.float32)
+    want = torch.full((2, 30000), -1, dtype=torch.int32, device="cuda")
+    ref.points_in_boxes_gpu(cuda(boxes), cuda(pts), want)
+    got = box_ops.points_in_boxes_gpu(cuda(pts), cuda(boxes))
+    assert (want >= 0).sum() > 3000 and torch.equal(got, want)
+
+
+def test_nms_wrapper_matches_model_nms_utils_contract():
+    """class_agnostic_nms call pattern (model_nms_utils.py:6-25): topk -> nms_gpu -> indices."""
+    boxes = cuda(synth.make_clustered_boxes(800, seed=51))
+    scores = torch.from_numpy(np.random.default_rng(5).uniform(size=800).astype(np.float32)).cuda()
+    top_scores, idx = torch.topk(scores, k=500)
+    keep, _ = box_ops.nms_gpu(boxes[idx][:, :7], top_scores, 0.7)
+    assert keep.dtype == torch.int64 and keep.is_cuda and keep.max() < 500
+    sel = boxes[idx][keep].cpu().numpy()
+    iou = oracle.boxes_bev_cpu(sel, sel)
+    np.fill_diagonal(iou, 0)
+    assert iou.max() <= 0.7 + 1e-3            # survivors do not suppress each other
+    empty, _ = box_ops.nms_gpu(boxes[:0], scores[:0], 0.7)
+    assert empty.numel() == 0

@@ -1,0 +1,155 @@
+"""a7/a8/a9 parity: sparse convolution through the C-ABI vs the CPU oracle (fp64 accumulation).
+Tolerances (BASELINE.json north_star): fp32 check mode max relative error 1e-4; bf16 tensor-core
+path 2e-2.  "max relative error" = max|got - want| / max|want| over the output tensor; the bf16 path is
+additionally held to an element-wise bound."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from com_b200 import ops, sparse
+from util import clustered_coords, random_coords
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-4
+TOL_BF16 = 2e-2
+
+
+def rel_err(got, want):
+    return float(np.abs(got.astype(np.float64) - want.astype(np.float64)).max() / max(np.abs(want).max(), 1e-30))
+
+
+def make_case(seed, n, Cin, Cout, ks=(3, 3, 3), st=(1, 1, 1), pd=(1, 1, 1), subm=True, batch=2, shape=(12, 40, 40)):
+    rng = np.random.default_rng(seed)
+    shape = list(shape)
+    coords = clustered_coords(rng, n, batch, shape, clusters=10, spread=2.5)
+    dl = (1, 1, 1)
+    if subm:
+        out_coords, nbr = coords, oracle.subm_nbrmap(coords, shape, ks)
+    else:
+        oshape = oracle.conv_out_shape(shape, ks, st, pd, dl)
+        out_coords = oracle.conv_out_coords(coords, oshape, ks, st, pd, dl)
+        nbr = oracle.nbrmap(out_coords, coords, shape, ks, st, pd, dl)
+    K = int(np.prod(ks))
+    feats = rng.normal(size=(len(coords), Cin)).astype(np.float32)
+    W = (rng.normal(size=(Cout, K, Cin)) / np.sqrt(K * Cin)).astype(np.float32)
+    return coords, out_coords, nbr, feats, W, rng
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("Cin,Cout", [(5, 16), (16, 16), (16, 32), (32, 32), (64, 64), (64, 128), (128, 128), (3, 7)])
+@pytest.mark.parametrize("subm", [True, False])
+def test_fwd_f32(Cin, Cout, subm):
+    coords, out_coords, nbr, feats, W, rng = make_case(Cin * 131 + Cout, 2500, Cin, Cout, st=(1, 1, 1) if subm else (2, 2, 2), subm=subm)
+    bias = rng.normal(size=(Cout,)).astype(np.float32)
+    want = oracle.conv_fwd(feats, W, nbr, bias)
+    got = ops.spconv_fwd_f32(cuda(feats), cuda(W), cuda(nbr), bias=cuda(bias)).cpu().numpy()
+    assert got.shape == want.shape and rel_err(got, want) < TOL_F32
+
+
+def test_fwd_f32_epilogue():
+    coords, out_coords, nbr, feats, W, rng = make_case(3, 2000, 16, 32)
+    no = nbr.shape[1]
+    bias, scale, shift = [rng.normal(size=(32,)).astype(np.float32) for _ in range(3)]
+    res = rng.normal(size=(no, 32)).astype(np.float32)
+    want = np.maximum((oracle.conv_fwd(feats, W, nbr, bias).astype(np.float64)) * scale + shift + res, 0)
+    got = ops.spconv_fwd_f32(cuda(feats), cuda(W), cuda(nbr), bias=cuda(bias), scale=cuda(scale), shift=cuda(shift),
+                             residual=cuda(res), relu=True).cpu().numpy()
+    assert rel_err(got, want.astype(np.float32)) < TOL_F32
+
+
+@pytest.mark.parametrize("Cin,Cout", [(5, 16), (16, 32), (64, 64), (128, 128)])
+@pytest.mark.parametrize("subm", [True, False])
+def test_bwd_f32(Cin, Cout, subm):
+    coords, out_coords, nbr, feats, W, rng = make_case(Cin + 7 * Cout, 2000, Cin, Cout, st=(1, 1, 1) if subm else (2, 2, 2), subm=subm)
+    dout = rng.normal(size=(nbr.shape[1], Cout)).astype(np.float32)
+    nbr_d = cuda(nbr)
+    nbr_t = ops.nbrmap_transpose(nbr_d, len(coords))
+    din = ops.spconv_dgrad_f32(cuda(dout), cuda(W), nbr_t).cpu().numpy()
+    dw = ops.spconv_wgrad_f32(cuda(feats), cuda(dout), nbr_d).cpu().numpy()
+    assert rel_err(din, oracle.conv_dgrad(dout, W, nbr, len(coords))) < TOL_F32
+    assert rel_err(dw, oracle.conv_wgrad(feats, dout, nbr)) < TOL_F32
+
+
+def bf16_round(a):
+    return torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+
+
+@pytest.mark.parametrize("Cin,Cout", [(5, 16), (16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128)])
+@pytest.mark.parametrize("subm", [True, False])
+def test_fwd_bf16_tensor_core(Cin, Cout, subm):
+    coords, out_coords, nbr, feats, W, rng = make_case(Cin * 17 + Cout, 3000, Cin, Cout, st=(1, 1, 1) if subm else (2, 2, 2), subm=subm)
+    fb, Wb = bf16_round(feats), bf16_round(W)
+    want = oracle.conv_fwd(fb, Wb, nbr)                 # same bf16-rounded operands, fp64 accumulate
+    x = ops.cast_pad(cuda(feats), ops.pad16(Cin))
+    wp = ops.pack_weight_bf16(cuda(W))
+    K = W.shape[1]
+    got32 = ops.spconv_fwd_bf16(x, wp, K, Cout, cuda(nbr), out_dtype=torch.float32).cpu().numpy()
+    assert rel_err(got32, want) < 1e-4                  # fp32 accumulation of exact bf16 products
+    got16 = ops.spconv_fwd_bf16(x, wp, K, Cout, cuda(nbr), out_dtype=torch.bfloat16).float().cpu().numpy()
+    assert rel_err(got16, want) < TOL_BF16
+    assert np.all(np.abs(got16 - want) <= 2.0 ** -8 * np.abs(want) + 1e-5 * np.abs(want).max())   # one bf16 rounding
+    # against the un-rounded fp32 problem the bf16 path stays inside the stated tolerance as well
+    assert rel_err(got16, oracle.conv_fwd(feats, W, nbr)) < TOL_BF16
+
+
+def test_fwd_bf16_epilogue_and_device_count():
+    coords, out_coords, nbr, feats, W, rng = make_case(11, 3000, 32, 32)
+    no = nbr.shape[1]
+    scale, shift = [rng.normal(size=(32,)).astype(np.float32) for _ in range(2)]
+    res = bf16_round(rng.normal(size=(no, 32)).astype(np.float32))
+    fb, Wb = bf16_round(feats), bf16_round(W)
+    want = np.maximum(oracle.conv_fwd(fb, Wb, nbr).astype(np.float64) * scale + shift + res, 0).astype(np.float32)
+    x = ops.cast_pad(cuda(feats), 32)
+    wp = ops.pack_weight_bf16(cuda(W))
+    n_dev = torch.tensor([no - 77], dtype=torch.int32, device="cuda")
+    out = torch.full((no, 32), -7.0, dtype=torch.bfloat16, device="cuda")
+    ops.spconv_fwd_bf16(x, wp, 27, 32, cuda(nbr), scale=cuda(scale), shift=cuda(shift),
+                        residual=cuda(res).to(torch.bfloat16), relu=True, no_dev=n_dev, out=out)
+    got = out.float().cpu().numpy()
+    assert rel_err(got[: no - 77], want[: no - 77]) < TOL_BF16
+    assert (got[no - 77:] == -7.0).all()                # rows beyond the device-side count are untouched
+
+
+def test_bf16_many_tiles_persistent_loop():
+    """More tiles than SMs: every CTA walks several tiles (pipeline phases wrap, TMEM double buffer)."""
+    rng = np.random.default_rng(12)
+    coords = random_coords(rng, 50000, 4, [16, 96, 96])
+    nbr = oracle.subm_nbrmap(coords, [16, 96, 96])
+    feats = rng.normal(size=(len(coords), 16)).astype(np.float32)
+    W = (rng.normal(size=(16, 27, 16)) / 20).astype(np.float32)
+    assert nbr.shape[1] > 148 * 128 * 2 and (nbr >= 0).mean() > 0.08
+    want = oracle.conv_fwd(bf16_round(feats), bf16_round(W), nbr)
+    got = ops.spconv_fwd_bf16(ops.cast_pad(cuda(feats), 16), ops.pack_weight_bf16(cuda(W)), 27, 16, cuda(nbr),
+                              out_dtype=torch.float32).cpu().numpy()
+    assert rel_err(got, want) < 1e-4
+
+
+def test_module_autograd_matches_oracle():
+    """SubMConv3d / SparseConv3d modules (spconv API) incl. backward through torch autograd."""
+    coords, out_coords, nbr, feats, W, rng = make_case(13, 1500, 16, 32, st=(2, 2, 2), subm=False)
+    conv = sparse.SparseConv3d(16, 32, 3, stride=2, padding=1, bias=True, indice_key="sp").cuda()
+    with torch.no_grad():
+        conv.weight.copy_(cuda(W).reshape(32, 3, 3, 3, 16))
+    bias = conv.bias.detach().cpu().numpy()
+    x = cuda(feats).requires_grad_(True)
+    t = sparse.SparseConvTensor(x, cuda(coords), [12, 40, 40], 2)
+    y = conv(t)
+    assert np.array_equal(y.indices.cpu().numpy(), out_coords) and y.spatial_shape == [6, 20, 20]
+    assert rel_err(y.features.detach().cpu().numpy(), oracle.conv_fwd(feats, W, nbr, bias)) < TOL_F32
+    dout = rng.normal(size=tuple(y.features.shape)).astype(np.float32)
+    y.features.backward(cuda(dout))
+    assert rel_err(x.grad.cpu().numpy(), oracle.conv_dgrad(dout, W, nbr, len(coords))) < TOL_F32
+    assert rel_err(conv.weight.grad.reshape(32, 27, 16).cpu().numpy(), oracle.conv_wgrad(feats, dout, nbr)) < TOL_F32
+    assert rel_err(conv.bias.grad.cpu().numpy(), dout.sum(0)) < TOL_F32
+    # SparseInverseConv3d re-uses the rulebook and returns to the input index set
+    inv = sparse.SparseInverseConv3d(32, 16, 3, indice_key="sp", bias=False).cuda()
+    z = inv(y)
+    assert np.array_equal(z.indices.cpu().numpy(), coords) and tuple(z.features.shape) == (len(coords), 16)
+    Wi = inv.weight.detach().reshape(16, 27, 32).cpu().numpy()
+    want = oracle.conv_fwd(y.features.detach().cpu().numpy(), Wi, ops.nbrmap_transpose(cuda(nbr), len(coords)).cpu().numpy())
+    assert rel_err(z.features.detach().cpu().numpy(), want) < TOL_F32

@@ -153,3 +153,18 @@ def test_dense_and_mean_vfe():
         vox[i, num[i]:] = 0
     want = torch.from_numpy(vox).sum(1) / torch.clamp_min(torch.from_numpy(num).float().view(-1, 1), 1.0)
     assert np.array_equal(oracle.mean_vfe(vox, num), want.numpy())    # mean_vfe.py:26-29
+
+
+def test_fast_cpu_baseline_matches_oracle():
+    """bench.py's CPU baseline (oracle/cpu_fast.c) computes the same conv as the fp64 oracle."""
+    rng = np.random.default_rng(2)
+    coords = clustered_coords(rng, 1500, 2, [10, 30, 30], 8, 2.0)
+    nbr = oracle.subm_nbrmap(coords, [10, 30, 30])
+    feats = rng.normal(size=(len(coords), 16)).astype(np.float32)
+    W = rng.normal(size=(32, 27, 16)).astype(np.float32) / 20
+    bias, scale, shift = [rng.normal(size=(32,)).astype(np.float32) for _ in range(3)]
+    res = rng.normal(size=(len(coords), 32)).astype(np.float32)
+    want = np.maximum(oracle.conv_fwd(feats, W, nbr, bias).astype(np.float64) * scale + shift + res, 0)
+    got = oracle.fast_conv_fwd(feats, W, nbr, bias, scale, shift, res, relu=True)
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
+    assert oracle.fast().orc_fast_threads() >= 1
