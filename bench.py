@@ -138,9 +138,13 @@ class EventProfiler:
         if tag == "hash_build":
             n = int(info["n_dev"].item()) if info["n_dev"] is not None else info["n"]
             return dict(n=min(n, info["n"]), slots=info["slots"])
-        if tag == "conv_out_coords":
+        if tag in ("conv_out_coords", "index_build"):
             n = int(info["n_dev"].item()) if info["n_dev"] is not None else info["n"]
             return dict(n=min(n, info["n"]), no=int(info["out_count"].item()), bitmap_bytes=info["bitmap_bytes"])
+        if tag == "index_rank":
+            return dict(n=info["n"])
+        if tag == "permute_rows":
+            return dict(n=info["n"], row_bytes=info["row_bytes"])
         return {}
 
     def times_ms(self):
@@ -169,6 +173,12 @@ def algorithmic(tag, m):
         return m["n"] * 16.0 + m["n"] * 8.0, 0.0
     if tag == "conv_out_coords":
         return m["n"] * 16.0 + m["no"] * 16.0, 0.0
+    if tag == "index_build":         # coords in, coords out, bitmap zeroed + read twice, prefix written + updated
+        return m["n"] * 16.0 + m["no"] * 16.0 + m["bitmap_bytes"] * 3.5, 0.0
+    if tag == "index_rank":
+        return m["n"] * 20.0, 0.0
+    if tag == "permute_rows":
+        return m["n"] * (2.0 * m["row_bytes"] + 4.0), 0.0
     return 0.0, 0.0
 
 
@@ -354,7 +364,8 @@ def ours(args):
                 "layers": {k: {"ms_per_launch": v["ms"] / v["n"], "tflops": v["flops"] / (v["ms"] / 1e3) / 1e12,
                                "gbs": v["bytes"] / (v["ms"] / 1e3) / 1e9} for k, v in conv_layers.items()}}
         hbm_kernels = {}
-        for tag in ("voxelize", "dense", "nbrmap_build", "hash_build", "conv_out_coords"):
+        for tag in ("voxelize", "dense", "nbrmap_build", "hash_build", "conv_out_coords", "index_build", "index_rank",
+                    "permute_rows"):
             if tag in fam and fam[tag]["ms"] > 0:
                 f = fam[tag]
                 g = f["bytes"] / (f["ms"] / 1e3) / 1e9

@@ -25,7 +25,7 @@ SIGNATURES = {
     "comb_sm_count": (c_int, []),
     "comb_launch_count": (c_longlong, []),
     "comb_voxelize_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "comb_voxelize": (c_int, [_P, _PI, c_int, c_int, _PF, _PF, c_int, c_int, _P, _P, _P, _P, c_int, c_int, c_int,
+    "comb_voxelize": (c_int, [_P, _PI, _P, c_int, c_int, c_int, _PF, _PF, c_int, c_int, _P, _P, _P, _P, c_int, c_int, c_int,
                               _P, _P, c_size_t, _P]),
     "comb_mean_vfe": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "comb_hash_slots": (c_int, [c_int]),
@@ -37,6 +37,14 @@ SIGNATURES = {
                                   c_int, _P]),
     "comb_nbrmap_transpose": (c_int, [_P, c_int, c_int, _P, c_int, _P, c_int, c_int, _P]),
     "comb_nbrmap_to_pairs": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, _P]),
+    "comb_index_bitmap_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "comb_index_prefix_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "comb_index_build": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _PI, _PI, _PI, _PI, _P, _P, _P, c_int, _P,
+                                 _P]),
+    "comb_index_rank": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "comb_nbrmap_build_indexed": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _PI, _PI, _PI, _PI, _P,
+                                          c_int, _P]),
+    "comb_permute_rows": (c_int, [_P, _P, c_int, _P, c_int, c_int, _P, _P]),
     "comb_spconv_fwd_f32": (c_int, [_P, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "comb_spconv_dgrad_f32": (c_int, [_P, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, _P]),
     "comb_spconv_wgrad_f32": (c_int, [_P, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, _P]),
@@ -44,6 +52,7 @@ SIGNATURES = {
     "comb_spconv_pack_weight_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "comb_spconv_fwd_bf16": (c_int, [_P, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P,
                                      c_int, _P]),
+    "comb_debug_conv_trace": (c_int, [_P]),
     "comb_affine_relu": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, _P, c_int, _P, _P]),
     "comb_cast_pad": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P]),
     "comb_dense": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),

@@ -15,13 +15,19 @@
 // There is no scatter and no atomic: each output row is owned by one CTA and written once with
 // bias / folded BatchNorm / residual / ReLU applied in the epilogue.
 //
-// Warp roles (288 threads):
-//   warps 0-3  producers : neighbour-index tile prefetch (cp.async 4 B, double buffered) and the
-//                          A gather (8 x 16 B cp.async per thread per chunk); thread 0 also streams
-//                          the pre-swizzled weight chunk with one cp.async.bulk (TMA engine).
-//   warps 4-7  epilogue  : tcgen05.ld 32 lanes x Cout columns -> registers -> epilogue -> global.
-//   warp  8    MMA       : lane 0 issues 4 x tcgen05.mma (M=128, N=Cout, K=16) per chunk, commits
-//                          to the stage's empty barrier; allocates / frees TMEM (2 accumulators).
+// Warp roles (704 threads, one CTA per SM, persistent over row tiles):
+//   warps 0-15 producers : neighbour-index tile prefetch (cp.async 4 B, double buffered) and the A gather through
+//                          registers: 2 x LDG.128 (only for neighbours that exist) -> 2 x STS.128 per thread per
+//                          chunk, software-pipelined one chunk deep; a warp instruction covers 32/PPO consecutive
+//                          rows of ONE kernel offset (few distinct 128-byte lines when rows are spatially ordered).
+//                          r1 profiles: one producer warp per sub-partition was issue-latency bound (~1100
+//                          cycles/chunk); cp.async tops out at ~17 B/clk/SM zero-fill included (~900 cycles/chunk).
+//   warps 16-19 epilogue : tcgen05.ld 32 lanes x Cout columns -> registers -> epilogue -> global.
+//   warp  20   MMA       : lane 0 issues 4 x tcgen05.mma (M=128, N=Cout, K=16) per chunk, commits to the
+//                          stage's empty barrier; allocates / frees TMEM (2 accumulators).
+//   warp  21   weights   : lane 0 streams the pre-swizzled weight chunk of every stage with cp.async.bulk, or,
+//                          when the whole packed image is <= 64 KB (Cin,Cout <= 32), loads it once and keeps it
+//                          resident.
 #include "common.cuh"
 
 namespace comb {
@@ -30,9 +36,19 @@ namespace {
 constexpr int kBM = 128;          // rows per tile (UMMA M)
 constexpr int kChunkK = 64;       // bf16 elements per K chunk (128 bytes)
 constexpr int kABytes = kBM * 128;
-constexpr int kProducers = 128;
-constexpr int kThreadsTC = 288;
+constexpr int kProdWarps = 16;    // gather warps: 4 groups of 4 warps; group g owns the chunks G with G % 4 == g
+constexpr int kProducers = kProdWarps * 32;
+constexpr int kGroups = 4;
+constexpr int kGroupThreads = kProducers / kGroups;       // 128: one thread per 16-byte column pair of 8 pieces
+constexpr int kGroupWarps = kProdWarps / kGroups;
+constexpr int kEpiWarp0 = kProdWarps;      // warps 16..19: (warp & 3) = TMEM lane quarter
+constexpr int kMmaWarp = kProdWarps + 4;   // warp 20
+// warp 21 (kProdWarps + 5): weight streamer
+constexpr int kIdxWarp = kProdWarps + 6;   // warp 22: neighbour-index tile prefetcher
+constexpr int kThreadsTC = (kProdWarps + 7) * 32;
+constexpr int kPiecesPerThread = (kBM * 8) / kGroupThreads;  // 8 x 16-byte pieces of one A chunk per group thread
 constexpr int kMaxK = 32;         // kernel offsets supported by the index tile
+constexpr int kBResidentMax = 64 * 1024;   // packed weights up to this size stay in shared memory for the whole kernel
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -59,7 +75,7 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
@@ -83,6 +99,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// Warp-uniform leader election: unlike `lane == 0` the compiler knows the predicate is uniform, so tcgen05
+// operands stay in uniform registers (the per-lane form costs a serialised R2UR loop per instruction).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -105,17 +128,35 @@ template <int CIN, int COUT>
 struct TcCfg {
   static constexpr int kOffPerChunk = CIN <= 64 ? 64 / CIN : 1;  // kernel offsets per K chunk
   static constexpr int kChunksPerOff = CIN <= 64 ? 1 : CIN / 64;
-  static constexpr int kPiecesPerOff = CIN <= 64 ? CIN / 8 : 8;   // 16-byte pieces of one offset inside a chunk
+  static constexpr int kPPO = CIN <= 64 ? CIN / 8 : 8;            // 16-byte pieces of one offset inside a chunk
   static constexpr int kBBytes = COUT * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = COUT >= 128 ? 5 : 6;
   static constexpr int kTmemCols = 2 * COUT < 32 ? 32 : 2 * COUT;
   static __host__ __device__ int num_chunks(int K) {
     return CIN <= 64 ? (K + kOffPerChunk - 1) / kOffPerChunk : K * kChunksPerOff;
   }
-  static size_t smem_bytes(int K) {
-    return 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 2 * (size_t)K * kBM * 4 + 256;
+  static __host__ __device__ int k_pad(int K) { return CIN <= 64 ? num_chunks(K) * kOffPerChunk : K; }
+  static __host__ __device__ bool b_resident(int K) { return (size_t)num_chunks(K) * kBBytes <= (size_t)kBResidentMax; }
+  // A pipeline stage holds S consecutive K chunks (A: S x 16 KB, plus their weight chunks when streamed) and is
+  // handed to the MMA warp as a whole: one barrier wait, 4*S tcgen05.mma and one commit per stage.  (r1 trace:
+  // with S = 1 the MMA warp's own loop — try_wait, descriptor arithmetic, 4 UTCHMMA, commit — took ~700 cycles
+  // per chunk and bounded every layer, whatever the producers did.)
+  static __host__ __device__ int sub_bytes(int K) { return kABytes + (b_resident(K) ? 0 : kBBytes); }
+  static __host__ __device__ int fixed_bytes(int K) {
+    return 1024 + 2 * k_pad(K) * kBM * 4 + (b_resident(K) ? num_chunks(K) * kBBytes : 0) + 512;
   }
+  static __host__ __device__ int subs(int K) {   // S: largest of 4, 2, 1 that still leaves two stages
+    const int avail = 225 * 1024 - fixed_bytes(K);
+    for (int S = 4; S > 1; S >>= 1)
+      if (avail / (S * sub_bytes(K)) >= 2 && num_chunks(K) >= S) return S;
+    return 1;
+  }
+  static __host__ __device__ int stage_bytes(int K) { return subs(K) * sub_bytes(K); }
+  static __host__ __device__ int stages(int K) {
+    int n = (225 * 1024 - fixed_bytes(K)) / stage_bytes(K);
+    const int cap = subs(K) >= 4 ? 2 : (subs(K) == 2 ? 4 : 8);
+    return n > cap ? cap : n;
+  }
+  static size_t smem_bytes(int K) { return (size_t)fixed_bytes(K) + (size_t)stages(K) * stage_bytes(K); }
 };
 
 struct TcParams {
@@ -132,14 +173,28 @@ struct TcParams {
   const __nv_bfloat16* residual;
   void* out;
   int out_f32;
+  long long* dbg;   // optional trace buffer (comb_debug_conv_trace), NULL in production
 };
+
+// trace layout: dbg[(G * 8 + slot)] for G < kDbgChunks, CTA 0 only; slots: 0 mma:full seen, 1 mma:issued+committed,
+// 2 prod(group of G, warp 0 of the group):loads issued, 3 prod:empty seen, 4 prod:stored+arrived, 5 epi: tile done (G = tile)
+constexpr int kDbgChunks = 512;
+__device__ __forceinline__ void dbg_stamp(long long* dbg, int G, int slot) {
+  if (dbg != nullptr && blockIdx.x == 0 && G < kDbgChunks) {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    dbg[G * 8 + slot] = t;
+  }
+}
+
+constexpr int kMaxStages = 8;
 
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(kThreadsTC, 1) spconv_tc_kernel(TcParams p) {
   using Cfg = TcCfg<CIN, COUT>;
-  constexpr int NS = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_full[NS], bar_empty[NS], bar_tfull[2], bar_tempty[2], bar_idx[2];
+  __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_tfull[2], bar_tempty[2], bar_idx[2],
+      bar_idx_free[2], bar_b;
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -147,96 +202,120 @@ __global__ void __launch_bounds__(kThreadsTC, 1) spconv_tc_kernel(TcParams p) {
   const int ntiles = (no + kBM - 1) / kBM;
   const int K = p.K;
   const int nchunks = Cfg::num_chunks(K);
+  const int kpad = Cfg::k_pad(K);
+  const bool bres = Cfg::b_resident(K);
+  const int NS = Cfg::stages(K);
+  const int S = Cfg::subs(K);                       // K chunks per pipeline stage
+  const int sub_bytes = Cfg::sub_bytes(K);
+  const int stage_bytes = S * sub_bytes;
+  const int nstages_tile = (nchunks + S - 1) / S;   // pipeline stages per row tile
+  const int nsub_pad = nstages_tile * S;            // chunk slots per tile (the last stage may be partial)
 
+  // shared memory map (1024-byte aligned):
+  //   [NS stages: S x A chunk (16 KB) | S x B chunk if streamed] [resident B] [index tiles 2 x kpad x 128 ints]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t idx_base = smem_base + NS * Cfg::kStageBytes;  // [2][K][128] ints
-  auto stageA = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
-  auto stageB = [&](int s) { return smem_base + s * Cfg::kStageBytes + kABytes; };
+  const uint32_t bres_base = smem_base + NS * stage_bytes;
+  const uint32_t idx_base = bres_base + (bres ? nchunks * Cfg::kBBytes : 0);
+  const uint32_t idx_buf_bytes = (uint32_t)kpad * kBM * 4;
+  const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), kProducers + 1);
+      mbar_init(smem_u32(&bar_full[s]), S * kGroupWarps + (bres ? 0 : 1));
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bar_tfull[a]), 1);
       mbar_init(smem_u32(&bar_tempty[a]), 4);
-      mbar_init(smem_u32(&bar_idx[a]), kProducers);
+      mbar_init(smem_u32(&bar_idx[a]), 32);
+      mbar_init(smem_u32(&bar_idx_free[a]), kGroups);
     }
+    mbar_init(smem_u32(&bar_b), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
                  "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // index-tile rows of the padding offsets (k in [K, kpad)) stay -1 for the whole kernel
+  for (int e = tid; e < 2 * (kpad - K) * kBM; e += kThreadsTC) {
+    const int buf = e / ((kpad - K) * kBM), r = e - buf * (kpad - K) * kBM;
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(idx_base + buf * idx_buf_bytes + (K * kBM + r) * 4), "r"(-1) : "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
 
-  if (warp < 4) {
-    // ===================== producers =====================
-    const uint8_t* in_bytes = reinterpret_cast<const uint8_t*>(p.in);
-    auto prefetch_idx = [&](int tile, int buf) {
-      const int row = tile * kBM + tid;
-      const uint32_t dst = idx_base + (uint32_t)buf * K * kBM * 4 + tid * 4;
-      if (tile < ntiles && row < no) {
-        for (int k = 0; k < K; ++k) cp_async4(dst + k * kBM * 4, p.nbr + (size_t)k * p.ld + row);
-      } else {
-        for (int k = 0; k < K; ++k) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + k * kBM * 4), "r"(-1) : "memory");
-      }
-      // arrives once the thread's cp.asyncs have landed (immediately when it only stored -1)
-      cp_async_mbar_arrive_noinc(smem_u32(&bar_idx[buf]));
-    };
-    int it = 0;
-    uint32_t g = 0;  // global chunk counter -> stage / phase
-    prefetch_idx(blockIdx.x, 0);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+  if (warp < kProdWarps) {
+    // ===================== producers: A gather (global/L2 -> registers -> swizzled shared memory) ==========
+    // Chunk slots are numbered G = it*nsub_pad + c over this CTA's tiles; group g (4 warps, 128 threads) owns the
+    // slots with G % 4 == g and moves the whole 128 x 128 B chunk: 8 x LDG.128 per thread (only for neighbours
+    // that exist) -> 8 x STS.128.  While one group waits for its loads the other three issue theirs.
+    // Piece e = j*128 + t:  piece-in-offset = t % PPO, row = ((j % PPO)*128 + t) / PPO, offset slot = j / PPO:
+    // a warp instruction covers 32/PPO CONSECUTIVE rows of ONE kernel offset — with rows in key order the
+    // gathered addresses are neighbours in memory (few 128-byte lines per instruction, L1 reuse across dx).
+    const int grp = warp / kGroupWarps, t = tid % kGroupThreads;
+    const uint8_t* src_base = reinterpret_cast<const uint8_t*>(p.in) + (t % Cfg::kPPO) * 16;
+    const int log2S = S == 4 ? 2 : (S == 2 ? 1 : 0);
+    int gs_prev = 0, s = 0;      // stage bookkeeping without divisions: gs = G >> log2S only ever grows
+    uint32_t ph = 0;
+    for (int it = 0; it < my_tiles; ++it) {
       const int buf = it & 1;
-      // all producers are done reading the other index buffer (used by the previous tile)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      prefetch_idx(tile + gridDim.x, buf ^ 1);
+      const uint32_t idx_tile = idx_base + (uint32_t)buf * idx_buf_bytes;
       mbar_wait(smem_u32(&bar_idx[buf]), (it >> 1) & 1);
-      const uint32_t idx_tile = idx_base + (uint32_t)buf * K * kBM * 4;
-      for (int c = 0; c < nchunks; ++c, ++g) {
-        const int s = g % NS;
-        const uint32_t ph = (g / NS) & 1;
-        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
-        const uint32_t a_base = stageA(s);
+      int c = (grp - it * nsub_pad) & (kGroups - 1);   // first chunk slot of this tile owned by the group
+      for (; c < nsub_pad; c += kGroups) {
+        const int G = it * nsub_pad + c;
+        const int gs = G >> log2S;               // global stage counter
+        const int sub = G & (S - 1);
+        s += gs - gs_prev;
+        gs_prev = gs;
+        while (s >= NS) { s -= NS; ph ^= 1u; }
+        uint4 v[kPiecesPerThread];
+        if (c < nchunks) {
+          const uint32_t idx_c =
+              idx_tile + (uint32_t)(CIN <= 64 ? c * Cfg::kOffPerChunk : c / Cfg::kChunksPerOff) * kBM * 4;
+          const uint32_t half = CIN > 64 ? (uint32_t)(c % Cfg::kChunksPerOff) * 128u : 0u;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int e = j * kProducers + tid;
-          const int r = e >> 3, q = e & 7;
-          int k, piece;
-          if constexpr (CIN <= 64) {
-            k = c * Cfg::kOffPerChunk + q / Cfg::kPiecesPerOff;
-            piece = q % Cfg::kPiecesPerOff;
-          } else {
-            k = c / Cfg::kChunksPerOff;
-            piece = (c % Cfg::kChunksPerOff) * 8 + q;
+          for (int j = 0; j < kPiecesPerThread; ++j) {
+            const int row = ((j % Cfg::kPPO) * kGroupThreads + t) / Cfg::kPPO, slot = j / Cfg::kPPO;
+            int rw;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw) : "r"(idx_c + (uint32_t)(slot * kBM + row) * 4) : "memory");
+            v[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (rw >= 0) v[j] = __ldg(reinterpret_cast<const uint4*>(src_base + (size_t)(uint32_t)rw * (CIN * 2) + half));
           }
-          int src_row = -1;
-          if (k < K) {
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(src_row) : "r"(idx_tile + (k * kBM + r) * 4) : "memory");
+        }
+        if (t == 0) dbg_stamp(p.dbg, G, 2);
+        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+        if (t == 0) dbg_stamp(p.dbg, G, 3);
+        if (c < nchunks) {   // padding slots of a partial last stage only arrive
+          const uint32_t a_base = smem_base + s * stage_bytes + sub * kABytes;
+#pragma unroll
+          for (int j = 0; j < kPiecesPerThread; ++j) {
+            const int row = ((j % Cfg::kPPO) * kGroupThreads + t) / Cfg::kPPO, slot = j / Cfg::kPPO;
+            const int q = slot * Cfg::kPPO + (t % Cfg::kPPO);           // 16-byte column of the 128-byte smem row
+            const uint32_t dst = a_base + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((q ^ (row & 7)) << 4));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[j].x), "r"(v[j].y), "r"(v[j].z),
+                         "r"(v[j].w)
+                         : "memory");
           }
-          const uint32_t dst = a_base + (r >> 3) * 1024 + (r & 7) * 128 + ((q ^ (r & 7)) << 4);
-          const uint8_t* src = in_bytes + (src_row >= 0 ? ((size_t)src_row * CIN * 2 + piece * 16) : 0);
-          cp_async16(dst, src, src_row >= 0 ? 16u : 0u);
         }
-        cp_async_mbar_arrive_noinc(smem_u32(&bar_full[s]));
-        if (tid == 0) {
-          mbar_arrive_expect_tx(smem_u32(&bar_full[s]), Cfg::kBBytes);
-          bulk_copy_g2s(stageB(s), p.wpacked + (size_t)c * Cfg::kBBytes, Cfg::kBBytes, smem_u32(&bar_full[s]));
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));   // release: the warp's stores happen-before the MMA warp's wait
+        if (t == 0) dbg_stamp(p.dbg, G, 4);
       }
+      // the group has issued (and consumed) all its index reads of this tile: hand the buffer back
+      asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(kGroupThreads) : "memory");
+      if (t == 0) mbar_arrive(smem_u32(&bar_idx_free[buf]));
     }
-  } else if (warp < 8) {
+  } else if (warp < kEpiWarp0 + 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const int a = it & 1;
       mbar_wait(smem_u32(&bar_tfull[a]), (it >> 1) & 1);
       tc_fence_after();
@@ -267,9 +346,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) spconv_tc_kernel(TcParams p) {
               const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                float2 t = __bfloat1622float2(r2[i]);
-                f[h * 8 + 2 * i] += t.x;
-                f[h * 8 + 2 * i + 1] += t.y;
+                float2 tt = __bfloat1622float2(r2[i]);
+                f[h * 8 + 2 * i] += tt.x;
+                f[h * 8 + 2 * i + 1] += tt.y;
               }
             }
           }
@@ -297,42 +376,103 @@ __global__ void __launch_bounds__(kThreadsTC, 1) spconv_tc_kernel(TcParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[a]));
+      if (warp == kEpiWarp0 && lane == 0) dbg_stamp(p.dbg, it, 5);
     }
-  } else {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B, N>>3 [17,23), M>>4 [24,29)
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-    int it = 0;
-    uint32_t g = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    int s = 0;
+    uint32_t ph = 0;
+    if (bres) mbar_wait(smem_u32(&bar_b), 0);
+    for (int it = 0; it < my_tiles; ++it) {
       const int a = it & 1;
       mbar_wait(smem_u32(&bar_tempty[a]), ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + a * COUT;
-      for (int c = 0; c < nchunks; ++c, ++g) {
-        const int s = g % NS;
-        mbar_wait(smem_u32(&bar_full[s]), (g / NS) & 1);
+      for (int st = 0; st < nstages_tile; ++st) {
+        mbar_wait(smem_u32(&bar_full[s]), ph);
+        if (lane == 0) dbg_stamp(p.dbg, (it * nstages_tile + st) * S, 0);
+        // the producers' st.shared (generic proxy) were acquired through the barrier; one proxy fence per stage
+        // makes them visible to the tensor core's async-proxy reads (r1 trace: a fence in every producer thread
+        // cost each gather group ~600 cycles per chunk)
         fence_proxy_async();
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t adesc = make_desc_sw128(stageA(s));
-          const uint64_t bdesc = make_desc_sw128(stageB(s));
+        const uint32_t stage_addr = smem_base + s * stage_bytes;
+        const int c0 = st * S;
+        const int nsub = nchunks - c0 < S ? nchunks - c0 : S;
+        if (elect_one_sync()) {
+          for (int sub = 0; sub < nsub; ++sub) {
+            const uint64_t adesc = make_desc_sw128(stage_addr + sub * kABytes);
+            const uint64_t bdesc = make_desc_sw128(bres ? bres_base + (c0 + sub) * Cfg::kBBytes
+                                                        : stage_addr + S * kABytes + sub * Cfg::kBBytes);
 #pragma unroll
-          for (int kk = 0; kk < kChunkK / 16; ++kk) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field
-            umma_bf16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < kChunkK / 16; ++kk) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field
+              umma_bf16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c0 | sub | kk) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(smem_u32(&bar_empty[s]));
-          if (c == nchunks - 1) umma_commit(smem_u32(&bar_tfull[a]));
+          if (st == nstages_tile - 1) umma_commit(smem_u32(&bar_tfull[a]));
         }
         __syncwarp();
+        if (lane == 0) dbg_stamp(p.dbg, (it * nstages_tile + st) * S, 1);
+        if (++s == NS) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == kIdxWarp) {
+    // ===================== neighbour-index prefetcher (warp 22) =====================
+    // idx[buf][k][r] = nbr[k][tile*128 + r] (-1 beyond the last row), double buffered one tile ahead.
+    const bool vec_ok = (p.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.nbr) & 15) == 0);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int buf = it & 1;
+      if (it >= 2) mbar_wait(smem_u32(&bar_idx_free[buf]), ((it - 2) >> 1) & 1);
+      const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * kBM + lane * 4;   // this lane: 4 consecutive rows
+      const uint32_t dst = idx_base + (uint32_t)buf * idx_buf_bytes + lane * 16;
+      if (vec_ok && row0 + 3 < no) {
+        for (int k = 0; k < K; ++k)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + k * kBM * 4),
+                       "l"(p.nbr + (size_t)k * p.ld + row0)
+                       : "memory");
+      } else {
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (row0 + q < no)
+              cp_async4(dst + k * kBM * 4 + q * 4, p.nbr + (size_t)k * p.ld + row0 + q);
+            else
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + k * kBM * 4 + q * 4), "r"(-1) : "memory");
+          }
+      }
+      cp_async_mbar_arrive_noinc(smem_u32(&bar_idx[buf]));   // fires when this lane's copies have landed
+    }
+  } else if (warp == kMmaWarp + 1 && lane == 0) {
+    // ===================== weight streamer (warp 21, one lane) =====================
+    if (bres) {
+      // small layers: the whole pre-swizzled weight image stays resident
+      const uint32_t bytes = (uint32_t)nchunks * Cfg::kBBytes;
+      mbar_arrive_expect_tx(smem_u32(&bar_b), bytes);
+      bulk_copy_g2s(bres_base, p.wpacked, bytes, smem_u32(&bar_b));
+    } else {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int st = 0; st < nstages_tile; ++st) {
+          const int c0 = st * S;
+          const int nsub = nchunks - c0 < S ? nchunks - c0 : S;
+          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+          mbar_arrive_expect_tx(smem_u32(&bar_full[s]), (uint32_t)nsub * Cfg::kBBytes);
+          bulk_copy_g2s(smem_base + s * stage_bytes + S * kABytes, p.wpacked + (size_t)c0 * Cfg::kBBytes,
+                        (uint32_t)nsub * Cfg::kBBytes, smem_u32(&bar_full[s]));
+          if (++s == NS) { s = 0; ph ^= 1; }
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");
@@ -374,7 +514,7 @@ int launch_tc(const TcParams& p, cudaStream_t stream) {
     COMB_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
     configured = true;
   }
-  if (smem > 227 * 1024 - 2048) {
+  if (smem > 227 * 1024 - 2048 || Cfg::stages(p.K) < 2) {
     set_error("comb_spconv_fwd_bf16: shared memory %zu exceeds the per-CTA limit", smem);
     return COMB_EINVAL;
   }
@@ -397,6 +537,8 @@ int dispatch_cout(int Cout, const TcParams& p, cudaStream_t stream) {
   return COMB_EINVAL;
 }
 
+static long long* g_conv_trace = nullptr;
+
 static int chunks_for(int Cin_p, int K) {
   return Cin_p <= 64 ? (K + 64 / Cin_p - 1) / (64 / Cin_p) : K * (Cin_p / 64);
 }
@@ -405,6 +547,13 @@ static int chunks_for(int Cin_p, int K) {
 }  // namespace comb
 
 using namespace comb;
+
+// Debug hook (not part of the product path): when set, CTA 0 of every following comb_spconv_fwd_bf16 launch
+// records clock64 stamps of its pipeline events for the first 512 chunks into buf (512*8 int64).
+extern "C" int comb_debug_conv_trace(void* buf) {
+  g_conv_trace = (long long*)buf;
+  return COMB_OK;
+}
 
 extern "C" size_t comb_spconv_packed_bytes(int Cin_p, int K, int Cout) {
   if (!(Cin_p == 16 || Cin_p == 32 || Cin_p == 64 || Cin_p == 128) || K < 1 || Cout < 8) return 0;
@@ -461,6 +610,7 @@ extern "C" int comb_spconv_fwd_bf16(const void* in_feats, int Cin_p, const void*
   p.residual = (const __nv_bfloat16*)residual;
   p.out = out;
   p.out_f32 = out_dtype == COMB_DT_F32;
+  p.dbg = g_conv_trace;
   switch (Cin_p) {
     case 16: return dispatch_cout<16>(Cout, p, stream);
     case 32: return dispatch_cout<32>(Cout, p, stream);

@@ -53,6 +53,23 @@ __global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__
   }
 }
 
+// one thread per 4-byte word of a row
+__global__ void __launch_bounds__(256) permute_rows_kernel(const uint32_t* __restrict__ in,
+                                                            const int* __restrict__ row_map, int n_max,
+                                                            const int* __restrict__ n_dev, int row_words, int scatter,
+                                                            uint32_t* __restrict__ out) {
+  const long long n = (long long)eff_n(n_max, n_dev) * row_words;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / row_words), w = (int)(e - (long long)r * row_words);
+    const int m = __ldg(row_map + r);
+    if (scatter) {
+      if (m >= 0) out[(size_t)m * row_words + w] = __ldg(in + e);
+    } else {
+      out[e] = m >= 0 ? __ldg(in + (size_t)m * row_words + w) : 0u;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) dense_index_kernel(const int4* __restrict__ coords, int n_max,
                                                            const int* __restrict__ n_dev, int batch, int D, int H,
                                                            int W, int* __restrict__ cell_row) {
@@ -100,6 +117,38 @@ __global__ void __launch_bounds__(256) dense_write_kernel(const T* __restrict__ 
   for (int c = warp; c < C; c += 8) o[(size_t)c * DHW] = any ? tile[lane * (C + 1) + c] : 0.0f;
 }
 
+// Vector variant (needs DHW % 4 == 0): a block owns 128 consecutive cells of one frame = 512 contiguous bytes
+// per channel.  Lane l of every warp owns cells 4l..4l+3 (their feature rows are read once, as one int4),
+// warp w writes channels w, w+8, ... with one 16-byte streaming store per lane: the whole tensor is written
+// exactly once in full 512-byte segments; feature rows of occupied cells are re-read from L1 (2 lines per row).
+constexpr int kCellsV = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(256) dense_write_vec_kernel(const T* __restrict__ feats,
+                                                               const int* __restrict__ cell_row, int C, int DHW,
+                                                               int tiles_per_frame, float* __restrict__ out) {
+  const int b = blockIdx.x / tiles_per_frame;
+  const int cell0 = (blockIdx.x - b * tiles_per_frame) * kCellsV;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cell = cell0 + lane * 4;
+  if (cell >= DHW) return;   // DHW % 4 == 0: a lane's four cells are all inside or all outside
+  const int4 r = __ldg(reinterpret_cast<const int4*>(cell_row + (size_t)b * DHW + cell));
+  float* o = out + (size_t)b * C * DHW + cell;
+  if ((r.x & r.y & r.z & r.w) < 0 && r.x < 0 && r.y < 0 && r.z < 0 && r.w < 0) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = warp; c < C; c += 8) __stcs(reinterpret_cast<float4*>(o + (size_t)c * DHW), z);
+    return;
+  }
+  for (int c = warp; c < C; c += 8) {
+    float4 v;
+    v.x = r.x >= 0 ? ld_as_float(feats, (size_t)r.x * C + c) : 0.0f;
+    v.y = r.y >= 0 ? ld_as_float(feats, (size_t)r.y * C + c) : 0.0f;
+    v.z = r.z >= 0 ? ld_as_float(feats, (size_t)r.z * C + c) : 0.0f;
+    v.w = r.w >= 0 ? ld_as_float(feats, (size_t)r.w * C + c) : 0.0f;
+    __stcs(reinterpret_cast<float4*>(o + (size_t)c * DHW), v);
+  }
+}
+
 static int ew_grid(long long work) {
   int g = cdiv(work, 256), cap = sm_count() * 16;
   return g < cap ? (g > 0 ? g : 1) : cap;
@@ -142,6 +191,19 @@ extern "C" int comb_cast_pad(const float* x, int n_max, const int* n_dev, int C,
   return COMB_OK;
 }
 
+extern "C" int comb_permute_rows(const void* in, const int* row_map, int n_max, const int* n_dev, int row_bytes,
+                                 int scatter, void* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(n_max >= 0 && row_bytes >= 4 && row_bytes % 4 == 0, "comb_permute_rows: bad shape");
+  if (n_max == 0) return COMB_OK;
+  COMB_CHECK_ARG(in && row_map && out, "comb_permute_rows: null pointer");
+  const int rw = row_bytes / 4;
+  permute_rows_kernel<<<ew_grid((long long)n_max * rw), 256, 0, stream>>>((const uint32_t*)in, row_map, n_max, n_dev, rw,
+                                                                         scatter, (uint32_t*)out);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}
+
 extern "C" size_t comb_dense_workspace_bytes(int batch, int D, int H, int W) {
   if (batch < 1 || D < 1 || H < 1 || W < 1) return 0;
   return align_up((size_t)batch * D * H * W * 4, 256);
@@ -163,6 +225,18 @@ extern "C" int comb_dense(const void* feats, int dtype, const int* coords, int n
     dense_index_kernel<<<cdiv(n_max, 256), 256, 0, stream>>>((const int4*)coords, n_max, n_dev, batch, D, H, W,
                                                              cell_row);
     COMB_LAUNCH_CHECK();
+  }
+  if (DHW % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (dtype == COMB_DT_F32 || dtype == COMB_DT_BF16)) {
+    const int tpf = cdiv(DHW, kCellsV);
+    const long long nb = (long long)tpf * batch;
+    COMB_CHECK_ARG(nb < (1ll << 31), "comb_dense: too many tiles");
+    if (dtype == COMB_DT_F32)
+      dense_write_vec_kernel<float><<<(unsigned)nb, 256, 0, stream>>>((const float*)feats, cell_row, C, DHW, tpf, out);
+    else
+      dense_write_vec_kernel<__nv_bfloat16><<<(unsigned)nb, 256, 0, stream>>>((const __nv_bfloat16*)feats, cell_row, C,
+                                                                              DHW, tpf, out);
+    COMB_LAUNCH_CHECK();
+    return COMB_OK;
   }
   const int tiles_per_frame = cdiv(DHW, kCells);
   const long long blocks = (long long)tiles_per_frame * batch;

@@ -27,8 +27,12 @@ constexpr int kMaxBatch = 32;
 constexpr int kChunk = 1024;          // points per block in K2/K4
 constexpr int kCandInf = 0x7F7F7F7F;  // memset(0x7F) pattern, larger than any point index
 
+// Frame offsets: either captured by value from host integers, or read from device memory (`dev`), which keeps
+// the launch sequence independent of the per-frame point counts (CUDA-graph replay with new inputs).
 struct Frames {
   int off[kMaxBatch + 1];
+  const int* dev;
+  __device__ __forceinline__ int at(int b) const { return dev ? __ldg(dev + b) : off[b]; }
 };
 
 struct VoxGeom {
@@ -54,8 +58,8 @@ __global__ void __launch_bounds__(256) vox_insert_kernel(const float* __restrict
                                                           int T, uint32_t* __restrict__ keys, int* __restrict__ cand,
                                                           uint32_t mask, int* __restrict__ slot_of_point) {
   const int frame = blockIdx.y;
-  const int i = fr.off[frame] + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= fr.off[frame + 1]) return;
+  const int i = fr.at(frame) + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= fr.at(frame + 1)) return;
   const float* p = points + (size_t)i * C;
   float xyz[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
   uint32_t key;
@@ -117,9 +121,9 @@ __global__ void __launch_bounds__(kChunk) vox_count_kernel(Frames fr, int T, con
                                                             const int* __restrict__ slot_of_point,
                                                             int* __restrict__ chunk_counts, int chunks_per_frame) {
   const int frame = blockIdx.y;
-  const int i = fr.off[frame] + blockIdx.x * kChunk + threadIdx.x;
+  const int i = fr.at(frame) + blockIdx.x * kChunk + threadIdx.x;
   bool first = false;
-  if (i < fr.off[frame + 1]) {
+  if (i < fr.at(frame + 1)) {
     int s = slot_of_point[i];
     first = (s >= 0) && (cand[(size_t)s * T] == i);
   }
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(1024) vox_scan_kernel(Frames fr, int batch, in
   if (threadIdx.x == 0) s_base = 0;
   __syncthreads();
   for (int b = 0; b < batch; ++b) {
-    const int nchunks = (fr.off[b + 1] - fr.off[b] + kChunk - 1) / kChunk;
+    const int nchunks = (fr.at(b + 1) - fr.at(b) + kChunk - 1) / kChunk;
     int running = 0;
     for (int c0 = 0; c0 < nchunks; c0 += 1024) {
       int c = c0 + threadIdx.x;
@@ -170,10 +174,10 @@ __global__ void __launch_bounds__(kChunk) vox_assign_kernel(Frames fr, VoxGeom g
                                                              int* __restrict__ voxel_slot, int* __restrict__ coords) {
   __shared__ int smem[33];
   const int frame = blockIdx.y;
-  const int i = fr.off[frame] + blockIdx.x * kChunk + threadIdx.x;
+  const int i = fr.at(frame) + blockIdx.x * kChunk + threadIdx.x;
   bool first = false;
   int s = -1;
-  if (i < fr.off[frame + 1]) {
+  if (i < fr.at(frame + 1)) {
     s = slot_of_point[i];
     first = (s >= 0) && (cand[(size_t)s * T] == i);
   }
@@ -308,7 +312,8 @@ extern "C" size_t comb_voxelize_workspace_bytes(int n_total, int batch, int max_
   return carve(nullptr, n_total, batch, max_voxels, max_points).bytes;
 }
 
-extern "C" int comb_voxelize(const float* points, const int* frame_offsets_host, int batch, int C,
+extern "C" int comb_voxelize(const float* points, const int* frame_offsets_host, const int* frame_offsets_dev,
+                             int n_cap, int batch, int C,
                              const float* vsize, const float* range, int max_points, int max_voxels, float* voxels,
                              int* coords, int* num_points, void* mean_out, int mean_dtype, int mean_c0, int mean_ld,
                              int* counts, void* workspace, size_t workspace_bytes, void* stream_) {
@@ -317,16 +322,25 @@ extern "C" int comb_voxelize(const float* points, const int* frame_offsets_host,
   COMB_CHECK_ARG(C >= 3, "comb_voxelize: points need >= 3 channels, got %d", C);
   COMB_CHECK_ARG(max_points >= 1 && max_voxels >= 1, "comb_voxelize: max_points/max_voxels must be >= 1");
   COMB_CHECK_ARG(coords && num_points && counts && workspace, "comb_voxelize: null output/workspace pointer");
-  COMB_CHECK_ARG(frame_offsets_host && vsize && range, "comb_voxelize: null host parameter pointer");
+  COMB_CHECK_ARG((frame_offsets_host || frame_offsets_dev) && vsize && range,
+                 "comb_voxelize: null host parameter pointer");
   Frames fr;
-  int max_frame = 0;
-  for (int b = 0; b <= batch; ++b) fr.off[b] = frame_offsets_host[b];
-  COMB_CHECK_ARG(fr.off[0] == 0, "comb_voxelize: frame_offsets[0] must be 0");
-  for (int b = 0; b < batch; ++b) {
-    COMB_CHECK_ARG(fr.off[b + 1] >= fr.off[b], "comb_voxelize: frame_offsets must be non-decreasing");
-    max_frame = fr.off[b + 1] - fr.off[b] > max_frame ? fr.off[b + 1] - fr.off[b] : max_frame;
+  int max_frame = 0, n_total = 0;
+  fr.dev = frame_offsets_dev;
+  if (frame_offsets_dev) {
+    // device-side offsets: every launch is sized for n_cap points per frame, surplus threads exit
+    COMB_CHECK_ARG(n_cap >= 0, "comb_voxelize: n_cap must be given with device-side frame offsets");
+    for (int b = 0; b <= batch; ++b) fr.off[b] = 0;
+    max_frame = n_total = n_cap;
+  } else {
+    for (int b = 0; b <= batch; ++b) fr.off[b] = frame_offsets_host[b];
+    COMB_CHECK_ARG(fr.off[0] == 0, "comb_voxelize: frame_offsets[0] must be 0");
+    for (int b = 0; b < batch; ++b) {
+      COMB_CHECK_ARG(fr.off[b + 1] >= fr.off[b], "comb_voxelize: frame_offsets must be non-decreasing");
+      max_frame = fr.off[b + 1] - fr.off[b] > max_frame ? fr.off[b + 1] - fr.off[b] : max_frame;
+    }
+    n_total = fr.off[batch];
   }
-  const int n_total = fr.off[batch];
   COMB_CHECK_ARG(n_total == 0 || points, "comb_voxelize: null points");
   VoxGeom g;
   for (int j = 0; j < 3; ++j) {

@@ -181,32 +181,33 @@ class VoxelResBackBone8x(nn.Module):
                                    shift=spec['shift'], residual=residual, relu=True, no_dev=n_dev)
 
     def _run_fused(self, feats, coords, batch_size, caps):
+        """Every level keeps its rows in KEY ORDER (ascending ((b*D+z)*H+y)*W+x): level 1 is permuted from
+        voxel order once, strided levels are emitted in key order by the bitmap index.  Spatially ordered rows
+        make the gathers of a 128-row tile hit neighbouring memory, and the bitmap-rank index replaces hashing."""
         plan = self._get_plan()
-        dev = feats.device
-        n1 = int(coords.shape[0])
         if feats.dtype == torch.bfloat16 and feats.shape[1] == 16:
             x = feats.contiguous()
         else:
             x = ops.cast_pad(feats.float().contiguous(), 16)
-        k3, one, zero = [3, 3, 3], [1, 1, 1], [0, 0, 0]
+        k3, one = [3, 3, 3], [1, 1, 1]
         shape = list(self.sparse_shape)
-        cur_coords, cur_n = coords.contiguous(), None
-        levels = []
-        counts = []
+        idx = ops.index_build(coords.contiguous(), batch_size, shape)
+        perm = ops.index_rank(coords, idx)
+        x = ops.permute_rows(x, perm, scatter=True)
+        cur_coords, cur_n = idx.coords, idx.count
+        levels, counts = [], [idx.count]
         for li in (1, 2, 3, 4):
             if li > 1:
                 spec = plan['down%d' % li]
                 conv = spec['conv']
-                oshape = ops.conv_out_shape(shape, conv.kernel_size, conv.stride, conv.padding, conv.dilation)
-                ocoords, ocnt = ops.conv_out_coords(cur_coords, batch_size, oshape, conv.kernel_size, conv.stride,
-                                                    conv.padding, conv.dilation, caps[li], n_dev=cur_n)
-                nbr_d = ops.nbrmap_build(ocoords, table, slots, batch_size, shape, conv.kernel_size, conv.stride,
-                                         conv.padding, conv.dilation, no_dev=ocnt)
-                x = self._conv(x, spec, nbr_d, ocnt)
-                cur_coords, cur_n, shape = ocoords, ocnt, oshape
-                counts.append(ocnt)
-            table, slots = ops.hash_build(cur_coords, batch_size, shape, n_dev=cur_n)
-            nbr = ops.nbrmap_build(cur_coords, table, slots, batch_size, shape, k3, one, one, one, no_dev=cur_n)
+                cv = (conv.kernel_size, conv.stride, conv.padding, conv.dilation)
+                oshape = ops.conv_out_shape(shape, *cv)
+                oidx = ops.index_build(cur_coords, batch_size, oshape, conv=cv, out_cap=caps[li], n_dev=cur_n)
+                nbr_d = ops.nbrmap_build_indexed(oidx.coords, idx, *cv, no_dev=oidx.count)
+                x = self._conv(x, spec, nbr_d, oidx.count)
+                idx, cur_coords, cur_n, shape = oidx, oidx.coords, oidx.count, oshape
+                counts.append(oidx.count)
+            nbr = ops.nbrmap_build_indexed(cur_coords, idx, k3, one, one, one, no_dev=cur_n)
             if li == 1:
                 x = self._conv(x, plan['input'], nbr, cur_n)
             for (c1, c2) in plan['res%d' % li]:
@@ -215,14 +216,13 @@ class VoxelResBackBone8x(nn.Module):
             levels.append((x, cur_coords, list(shape)))
         spec = plan['out']
         conv = spec['conv']
-        oshape = ops.conv_out_shape(shape, conv.kernel_size, conv.stride, conv.padding, conv.dilation)
-        ocoords, ocnt = ops.conv_out_coords(cur_coords, batch_size, oshape, conv.kernel_size, conv.stride,
-                                            conv.padding, conv.dilation, caps[5], n_dev=cur_n)
-        nbr_d = ops.nbrmap_build(ocoords, table, slots, batch_size, shape, conv.kernel_size, conv.stride,
-                                 conv.padding, conv.dilation, no_dev=ocnt)
-        x = self._conv(x, spec, nbr_d, ocnt)
-        counts.append(ocnt)
-        levels.append((x, ocoords, list(oshape)))
+        cv = (conv.kernel_size, conv.stride, conv.padding, conv.dilation)
+        oshape = ops.conv_out_shape(shape, *cv)
+        oidx = ops.index_build(cur_coords, batch_size, oshape, conv=cv, out_cap=caps[5], n_dev=cur_n)
+        nbr_d = ops.nbrmap_build_indexed(oidx.coords, idx, *cv, no_dev=oidx.count)
+        x = self._conv(x, spec, nbr_d, oidx.count)
+        counts.append(oidx.count)
+        levels.append((x, oidx.coords, list(oshape)))
         return levels, torch.cat(counts)
 
     def _caps(self, n1, batch_size, worst):
@@ -244,20 +244,23 @@ class VoxelResBackBone8x(nn.Module):
         return caps
 
     def forward_fused(self, feats, coords, batch_size):
-        """-> (x_conv1, x_conv2, x_conv3, x_conv4, out) SparseConvTensors with bf16 features."""
+        """-> (x_conv1, x_conv2, x_conv3, x_conv4, out) SparseConvTensors with bf16 features.
+        All five tensors have their rows in key order (x_conv1 is therefore a row permutation of the input
+        voxels: same (index, feature) pairs as spconv's, different row order; nothing downstream of the
+        backbone in the reference depends on the row order)."""
         if not feats.is_cuda:
             raise RuntimeError("VoxelResBackBone8x needs CUDA tensors (no CPU fallback)")
         n1 = int(coords.shape[0])
         caps = self._caps(n1, batch_size, worst=False)
         levels, counts = self._run_fused(feats, coords, batch_size, caps)
         cnt = counts.tolist()                      # the only host sync of the fused path
-        if any(c >= caps[li] for c, li in zip(cnt, (2, 3, 4, 5))):
+        if any(c >= caps[li] for c, li in zip(cnt[1:], (2, 3, 4, 5))):
             caps = self._caps(n1, batch_size, worst=True)
             levels, counts = self._run_fused(feats, coords, batch_size, caps)
             cnt = counts.tolist()
-        for c, li in zip(cnt, (2, 3, 4, 5)):
+        for c, li in zip(cnt[1:], (2, 3, 4, 5)):
             self._ratios[li] = max(self._ratios.get(li, 0.0), c / max(n1, 1))
-        ns = [n1] + cnt
+        ns = cnt                                   # cnt[0] = unique level-1 voxels (== n1 for a voxelizer output)
         outs = []
         for (x, c, shape), n in zip(levels, ns):
             outs.append(SparseConvTensor(x[:n], c[:n], shape, batch_size))

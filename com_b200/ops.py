@@ -89,9 +89,16 @@ def voxelize(points, frame_offsets, vsize_xyz, range_xyz, max_points, max_voxels
     """
     lib = _lib.load()
     _need(points, torch.float32, "points")
-    batch = len(frame_offsets) - 1
     n_total, C = int(points.shape[0]), int(points.shape[1])
-    assert frame_offsets[-1] == n_total, "frame_offsets[-1] must equal the number of points"
+    offs_dev = None
+    if isinstance(frame_offsets, torch.Tensor):
+        # device-side offsets (int32, batch+1): points.shape[0] is the capacity, off[batch] <= capacity
+        _need(frame_offsets, torch.int32, "frame_offsets")
+        offs_dev = frame_offsets
+        batch = int(frame_offsets.shape[0]) - 1
+    else:
+        batch = len(frame_offsets) - 1
+        assert frame_offsets[-1] == n_total, "frame_offsets[-1] must equal the number of points"
     dev = points.device
     cap = batch * max_voxels
     voxels = torch.empty((cap, max_points, C), dtype=torch.float32, device=dev) if want_voxels else None
@@ -106,12 +113,12 @@ def voxelize(points, frame_offsets, vsize_xyz, range_xyz, max_points, max_voxels
         mdt = _dt(mean)
     ws_bytes = lib.comb_voxelize_workspace_bytes(n_total, batch, max_voxels, max_points)
     ws = _ws(ws_bytes, dev)
-    offs = (ctypes.c_int * (batch + 1))(*[int(x) for x in frame_offsets])
+    offs = None if offs_dev is not None else (ctypes.c_int * (batch + 1))(*[int(x) for x in frame_offsets])
     vs = (ctypes.c_float * 3)(*[float(np.float32(x)) for x in vsize_xyz])
     rg = (ctypes.c_float * 6)(*[float(np.float32(x)) for x in range_xyz])
     with _Scope("voxelize", n=n_total, C=C, T=int(max_points), counts=counts, batch=batch,
                 want_voxels=want_voxels, mean_ld=int(mean_ld or 0), mean_bytes=(mean.element_size() if mean is not None else 0)):
-        check(lib.comb_voxelize(_p(points), offs, batch, C, vs, rg, int(max_points), int(max_voxels), _p(voxels),
+        check(lib.comb_voxelize(_p(points), offs, _p(offs_dev), n_total, batch, C, vs, rg, int(max_points), int(max_voxels), _p(voxels),
                                 _p(coords), _p(num), _p(mean), mdt, int(mean_c0), int(mean_ld or 1), _p(counts), _p(ws),
                                 ws.numel(), _stream()), "comb_voxelize")
     return dict(voxels=voxels, coords=coords, num_points=num, counts=counts, mean=mean)
@@ -209,6 +216,79 @@ def nbrmap_to_pairs(nbr, no_dev=None):
     check(lib.comb_nbrmap_to_pairs(_p(nbr), K, ld, _p(no_dev), ld, _p(pairs), _p(num), _stream()),
           "comb_nbrmap_to_pairs")
     return pairs, num
+
+
+class GridIndex:
+    """Bitmap-rank index of one level (rows in ascending key order). See comb_index_build."""
+
+    def __init__(self, bitmap, prefix, batch, shape, coords, count):
+        self.bitmap, self.prefix, self.batch, self.shape = bitmap, prefix, int(batch), [int(x) for x in shape]
+        self.coords, self.count = coords, count          # (cap,4) int32 rows in key order, device int32[1]
+
+
+def index_build(coords, batch, shape, conv=None, out_cap=None, n_dev=None, want_coords=True):
+    """Index of `coords` (conv=None; shape = their grid) or of the output set of the strided conv
+    conv=(ksize, stride, pad, dil) applied to them (shape = the OUTPUT grid)."""
+    lib = _lib.load()
+    _need(coords, torch.int32, "coords")
+    _need(n_dev, torch.int32, "n_dev")
+    dev = coords.device
+    D, H, W = [int(x) for x in shape]
+    n = int(coords.shape[0])
+    bitmap = torch.empty((max(lib.comb_index_bitmap_bytes(int(batch), D, H, W), 256),), dtype=torch.uint8, device=dev)
+    prefix = torch.empty((max(lib.comb_index_prefix_bytes(int(batch), D, H, W), 256),), dtype=torch.uint8, device=dev)
+    out_cap = int(n if out_cap is None else out_cap)
+    out = torch.empty((max(out_cap, 1), 4), dtype=torch.int32, device=dev) if want_coords else None
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+    cv = [None] * 4 if conv is None else [int3(v) for v in conv]
+    with _Scope("index_build", n=n, n_dev=n_dev, out_count=cnt, bitmap_bytes=int(bitmap.numel())):
+        check(lib.comb_index_build(_p(coords), n, _p(n_dev), int(batch), D, H, W, cv[0], cv[1], cv[2], cv[3],
+                                   _p(bitmap), _p(prefix), _p(out), out_cap, _p(cnt), _stream()), "comb_index_build")
+    return GridIndex(bitmap, prefix, batch, shape, out, cnt)
+
+
+def index_rank(coords, index, n_dev=None):
+    """Row of every coordinate in the index (-1 when absent)."""
+    lib = _lib.load()
+    _need(coords, torch.int32, "coords")
+    n = int(coords.shape[0])
+    rows = torch.empty((n,), dtype=torch.int32, device=coords.device)
+    D, H, W = index.shape
+    with _Scope("index_rank", n=n):
+        check(lib.comb_index_rank(_p(coords), n, _p(n_dev), index.batch, D, H, W, _p(index.bitmap), _p(index.prefix),
+                                  _p(rows), _stream()), "comb_index_rank")
+    return rows
+
+
+def nbrmap_build_indexed(out_coords, index, ksize, stride, pad, dil, no_dev=None, ld=None):
+    """Gather-form rulebook against the bitmap-rank index of the INPUT level."""
+    lib = _lib.load()
+    _need(out_coords, torch.int32, "out_coords")
+    _need(no_dev, torch.int32, "no_dev")
+    no = int(out_coords.shape[0])
+    ld = int(ld or no)
+    K = int(ksize[0]) * int(ksize[1]) * int(ksize[2])
+    nbr = torch.empty((K, ld), dtype=torch.int32, device=out_coords.device)
+    iD, iH, iW = index.shape
+    with _Scope("nbrmap_build", no=no, no_dev=no_dev, K=K, nbr=nbr):
+        check(lib.comb_nbrmap_build_indexed(_p(out_coords), no, _p(no_dev), _p(index.bitmap), _p(index.prefix),
+                                            index.batch, iD, iH, iW, int3(ksize), int3(stride), int3(pad), int3(dil),
+                                            _p(nbr), ld, _stream()), "comb_nbrmap_build_indexed")
+    return nbr
+
+
+def permute_rows(x, row_map, scatter, n_out=None, n_dev=None):
+    """scatter: out[row_map[r]] = x[r];  gather: out[r] = x[row_map[r]] (negative map entries: skipped / zero)."""
+    lib = _lib.load()
+    _need(x, x.dtype, "x")
+    _need(row_map, torch.int32, "row_map")
+    n = int(row_map.shape[0])
+    row_bytes = int(x.shape[1]) * x.element_size()
+    out = torch.empty((int(n_out if n_out is not None else n), int(x.shape[1])), dtype=x.dtype, device=x.device)
+    with _Scope("permute_rows", n=n, row_bytes=row_bytes):
+        check(lib.comb_permute_rows(_p(x), _p(row_map), n, _p(n_dev), row_bytes, int(bool(scatter)), _p(out), _stream()),
+              "comb_permute_rows")
+    return out
 
 
 # --------------------------------------------------------------------------------------------- sparse conv

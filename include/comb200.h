@@ -62,7 +62,10 @@ long long comb_launch_count(void);
  * each voxel keeps its first `max_points` points in point order.
  *
  * points       [n_total, C] fp32, frames concatenated.
- * frame_offsets_host [batch+1] host ints, frame b = rows [off[b], off[b+1]).
+ * frame_offsets_host [batch+1] host ints, frame b = rows [off[b], off[b+1]);  OR
+ * frame_offsets_dev  [batch+1] device ints with the same meaning (host pointer ignored): the launch sequence
+ *              then depends only on n_cap (an upper bound of off[batch], also used to size the workspace), so
+ *              the call can be captured in a CUDA graph and replayed with different frames.
  * voxels       [batch*max_voxels, max_points, C] fp32 or NULL (rows [0,total) written, zero padded)
  * coords       [batch*max_voxels, 4] int32 (b, z, y, x); frames are packed back to back
  * num_points   [batch*max_voxels] int32
@@ -72,7 +75,8 @@ long long comb_launch_count(void);
  * workspace    comb_voxelize_workspace_bytes(...) bytes, 256-byte aligned.
  */
 size_t comb_voxelize_workspace_bytes(int n_total, int batch, int max_voxels, int max_points);
-int comb_voxelize(const float* points, const int* frame_offsets_host, int batch, int C,
+int comb_voxelize(const float* points, const int* frame_offsets_host, const int* frame_offsets_dev, int n_cap,
+                  int batch, int C,
                   const float* vsize_xyz_host, const float* range_xyz_host,
                   int max_points, int max_voxels,
                   float* voxels, int* coords, int* num_points,
@@ -126,6 +130,30 @@ int comb_nbrmap_transpose(const int* nbr, int K, int no_max, const int* no_dev, 
 int comb_nbrmap_to_pairs(const int* nbr, int K, int no_max, const int* no_dev, int ld,
                          int* pairs, int* pair_num, void* stream);
 
+/* ---- a6 (fused pipeline): bitmap-rank grid index ----------------------------------------------
+ * Rows of every level are kept in canonical order (ascending linear key), so the coordinate index of a
+ * level is a bitmap over the grid (1 bit per cell) plus the number of set bits before every 32-byte
+ * block: row(key) = prefix[key>>8] + popcount of the block's bits below key.  No hash table, no sort.
+ *
+ * comb_index_build: ksize == NULL -> index of `coords` themselves (D,H,W = their grid);
+ *                   ksize != NULL -> index of the OUTPUT set of the strided conv (ksize,stride,pad,dil)
+ *                                    applied to `coords` (D,H,W = the output grid).
+ *   bitmap [comb_index_bitmap_bytes], prefix [comb_index_prefix_bytes]; out_coords (nullable)
+ *   [out_cap,4] receives the rows in key order, out_count (device int) their number (clamped to out_cap).
+ * comb_index_rank: rows[i] = row of coords[i] in the index, -1 if absent (voxel order -> key order).
+ * comb_nbrmap_build_indexed: same contract as comb_nbrmap_build with the index of the INPUT level. */
+size_t comb_index_bitmap_bytes(int batch, int D, int H, int W);
+size_t comb_index_prefix_bytes(int batch, int D, int H, int W);
+int comb_index_build(const int* coords, int n_max, const int* n_dev, int batch, int D, int H, int W,
+                     const int* ksize, const int* stride, const int* pad, const int* dil,
+                     void* bitmap, void* prefix, int* out_coords, int out_cap, int* out_count, void* stream);
+int comb_index_rank(const int* coords, int n_max, const int* n_dev, int batch, int D, int H, int W,
+                    const void* bitmap, const void* prefix, int* rows, void* stream);
+int comb_nbrmap_build_indexed(const int* out_coords, int no_max, const int* no_dev,
+                              const void* bitmap, const void* prefix, int batch, int iD, int iH, int iW,
+                              const int* ksize, const int* stride, const int* pad, const int* dil,
+                              int* nbr, int ld, void* stream);
+
 /* ---- a7/a8/a9: sparse convolution ------------------------------------------------------------
  * Replaces the gather-GEMM-scatter of spconv's SparseConvolution.forward/backward.
  * Weights are in spconv-2.x layout [Cout, K, Cin] (= (Cout,kz,ky,kx,Cin), one of the layouts
@@ -163,12 +191,21 @@ int comb_spconv_fwd_bf16(const void* in_feats, int Cin_p, const void* wpacked, i
                          int epi_flags, const float* bias, const float* scale, const float* shift,
                          const void* residual, void* out, int out_dtype, void* stream);
 
+/* Debug hook: CTA 0 of every following comb_spconv_fwd_bf16 launch records clock64 stamps of its pipeline
+ * events (first 512 chunks, 8 int64 slots each) into `buf` (device, 32 KB); NULL switches tracing off. */
+int comb_debug_conv_trace(void* buf);
+
 /* Elementwise helpers used between convolutions (a9: BatchNorm1d(eval) + ReLU + residual). */
 int comb_affine_relu(const void* x, int dtype, int n_max, const int* n_dev, int C,
                      const float* scale, const float* shift, const void* residual, int relu,
                      void* out, void* stream);
 int comb_cast_pad(const float* x, int n_max, const int* n_dev, int C, void* out_bf16, int ld,
                   void* stream);
+/* Row permutation: out[row_map[r], :] = in[r, :] (scatter=1) or out[r, :] = in[row_map[r], :] (scatter=0) for
+ * r < n; rows whose map entry is negative are skipped (scatter) / zero filled (gather).  `row_bytes` is
+ * a multiple of 4.  Used to move features between voxel order and key order. */
+int comb_permute_rows(const void* in, const int* row_map, int n_max, const int* n_dev, int row_bytes,
+                      int scatter, void* out, void* stream);
 
 /* ---- a10: HeightCompression / SparseConvTensor.dense() ---------------------------------------
  * Replaces encoded_spconv_tensor.dense() (pcdet/models/backbones_2d/map_to_bev/

@@ -20,6 +20,11 @@ def rel_err(got, want):
     return float(np.abs(got.astype(np.float64) - want).max() / max(np.abs(want).max(), 1e-30))
 
 
+def key_order(coords, shape):
+    c = coords.astype(np.int64)
+    return np.argsort(((c[:, 0] * shape[0] + c[:, 1]) * shape[1] + c[:, 2]) * shape[2] + c[:, 3], kind="stable")
+
+
 def bf16_rnd(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).float().numpy()
 
@@ -88,6 +93,8 @@ def test_fused_bf16_vs_oracle(setup):
     errs = []
     for t, (wf, wc, wshape), (ef, _, _) in zip(got_levels, ref_levels, emu_levels):
         assert t.features.dtype == torch.bfloat16 and t.spatial_shape == wshape
+        o = key_order(wc, wshape)       # the fused path keeps rows in key order (level 1 of the oracle: voxel order)
+        wf, wc, ef = wf[o], wc[o], ef[o]
         assert np.array_equal(t.indices.cpu().numpy(), wc)                 # rulebook outputs are bit-exact
         g = t.features.float().cpu().numpy()
         errs.append((rel_err(g, ef), rel_err(g, wf)))
@@ -112,7 +119,8 @@ def test_waymo_shape_batch_properties():
         ref_c.append(np.concatenate([np.full((len(c), 1), b, np.int32), c], axis=1))
     assert np.array_equal(vc, np.concatenate(ref_c))
     x1 = bd["multi_scale_3d_features"]["x_conv1"]
-    assert np.array_equal(x1.indices.cpu().numpy(), vc)                    # SubM keeps rows
+    o1 = key_order(vc, [41, 1504, 1504])
+    assert np.array_equal(x1.indices.cpu().numpy(), vc[o1])                # same voxel set, rows in key order
     shapes = [bd["multi_scale_3d_features"][n].spatial_shape for n in ("x_conv1", "x_conv2", "x_conv3", "x_conv4")]
     assert shapes == [[41, 1504, 1504], [21, 752, 752], [11, 376, 376], [5, 188, 188]]
     enc = bd["encoded_spconv_tensor"]
@@ -135,11 +143,14 @@ def test_waymo_shape_batch_properties():
     f0 = pipe.forward_host(frames[:1])
     lv, _, _ = cpu_pipeline.frame_forward(frames[:1], sd, synth.VOXEL_SIZE, synth.POINT_CLOUD_RANGE, 5, 150000,
                                           conv=oracle.fast_conv_fwd, want_dense=False)
-    for n, (wf, wc, _) in zip(("x_conv1", "x_conv2", "x_conv3", "x_conv4"), lv):
+    for n, (wf, wc, ws) in zip(("x_conv1", "x_conv2", "x_conv3", "x_conv4"), lv):
         t = f0["multi_scale_3d_features"][n]
+        o = key_order(wc, ws)
+        wf, wc = wf[o], wc[o]
         assert np.array_equal(t.indices.cpu().numpy(), wc)
         assert rel_err(t.features.float().cpu().numpy(), wf) < 2e-2
     assert np.array_equal(f0["encoded_spconv_tensor"].indices.cpu().numpy(), lv[4][1])
     assert rel_err(f0["encoded_spconv_tensor"].features.float().cpu().numpy(), lv[4][0]) < 2e-2
-    # a frame's result does not depend on what else is in the batch (shardability)
+    # a frame's result does not depend on what else is in the batch (shardability):
+    # key order puts frame 0 first
     assert torch.equal(x1.features[:n0], f0["multi_scale_3d_features"]["x_conv1"].features)

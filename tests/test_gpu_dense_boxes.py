@@ -24,16 +24,17 @@ def gold():
     return np.load(os.path.join(GOLDEN, "box_ops_ref.npz"))
 
 
+@pytest.mark.parametrize("shape", [[2, 47, 45], [2, 188, 188], [3, 20, 36]])    # DHW % 4 != 0 and == 0 (vector path)
 @pytest.mark.parametrize("C,dtype", [(128, torch.float32), (128, torch.bfloat16), (5, torch.float32), (33, torch.float32)])
-def test_dense(C, dtype):
+def test_dense(C, dtype, shape):
     rng = np.random.default_rng(C)
-    batch, shape = 3, [2, 47, 45]
+    batch = 3
     coords = random_coords(rng, 2500, batch, shape)
     feats = rng.normal(size=(len(coords), C)).astype(np.float32)
     f = cuda(feats).to(dtype)
     got = ops.dense(f, cuda(coords), batch, shape).cpu().numpy()
     want = oracle.dense(f.float().cpu().numpy(), coords, batch, shape)
-    assert got.shape == (batch, C, 2, 47, 45) and np.array_equal(got, want)
+    assert got.shape == (batch, C, *shape) and np.array_equal(got, want)
     empty = ops.dense(f[:0], cuda(coords[:0]), batch, shape)
     assert float(empty.abs().sum()) == 0.0
 
