@@ -180,7 +180,7 @@ class VoxelResBackBone8x(nn.Module):
         return ops.spconv_fwd_bf16(x, spec['w'], spec['K'], spec['cout'], nbr, scale=spec['scale'],
                                    shift=spec['shift'], residual=residual, relu=True, no_dev=n_dev)
 
-    def _run_fused(self, feats, coords, batch_size, caps):
+    def _run_fused(self, feats, coords, batch_size, caps, n_dev=None):
         """Every level keeps its rows in KEY ORDER (ascending ((b*D+z)*H+y)*W+x): level 1 is permuted from
         voxel order once, strided levels are emitted in key order by the bitmap index.  Spatially ordered rows
         make the gathers of a 128-row tile hit neighbouring memory, and the bitmap-rank index replaces hashing."""
@@ -191,9 +191,9 @@ class VoxelResBackBone8x(nn.Module):
             x = ops.cast_pad(feats.float().contiguous(), 16)
         k3, one = [3, 3, 3], [1, 1, 1]
         shape = list(self.sparse_shape)
-        idx = ops.index_build(coords.contiguous(), batch_size, shape)
-        perm = ops.index_rank(coords, idx)
-        x = ops.permute_rows(x, perm, scatter=True)
+        idx = ops.index_build(coords.contiguous(), batch_size, shape, n_dev=n_dev)
+        perm = ops.index_rank(coords, idx, n_dev=n_dev)
+        x = ops.permute_rows(x, perm, scatter=True, n_dev=n_dev)
         cur_coords, cur_n = idx.coords, idx.count
         levels, counts = [], [idx.count]
         for li in (1, 2, 3, 4):
@@ -243,28 +243,38 @@ class VoxelResBackBone8x(nn.Module):
             prev = caps[li]
         return caps
 
+    def fused_async(self, feats, coords, batch_size, n_dev=None, worst=False):
+        """Enqueue the whole fused backbone without any host synchronisation.
+        feats/coords may be capacity-sized with the real row count in `n_dev` (device int32[1]).
+        -> (levels [(features, coords, shape)] x5 capacity-sized, counts device int32[5], caps)."""
+        if not feats.is_cuda:
+            raise RuntimeError("VoxelResBackBone8x needs CUDA tensors (no CPU fallback)")
+        caps = self._caps(int(coords.shape[0]), batch_size, worst=worst)
+        levels, counts = self._run_fused(feats, coords, batch_size, caps, n_dev=n_dev)
+        return levels, counts, caps
+
+    def fused_finish(self, levels, cnt, caps, n1, batch_size):
+        """cnt: the five row counts on the host.  Returns the SparseConvTensors, or None when a capacity
+        overflowed (the caller re-runs with worst-case capacities)."""
+        hard = self._caps(n1, batch_size, worst=True)     # a capacity equal to the hard bound cannot overflow
+        if any(c >= caps[li] and caps[li] < hard[li] for c, li in zip(cnt[1:], (2, 3, 4, 5))):
+            return None
+        for c, li in zip(cnt[1:], (2, 3, 4, 5)):
+            self._ratios[li] = max(self._ratios.get(li, 0.0), c / max(n1, 1))
+        return tuple(SparseConvTensor(x[:n], c[:n], shape, batch_size) for (x, c, shape), n in zip(levels, cnt))
+
     def forward_fused(self, feats, coords, batch_size):
         """-> (x_conv1, x_conv2, x_conv3, x_conv4, out) SparseConvTensors with bf16 features.
         All five tensors have their rows in key order (x_conv1 is therefore a row permutation of the input
         voxels: same (index, feature) pairs as spconv's, different row order; nothing downstream of the
         backbone in the reference depends on the row order)."""
-        if not feats.is_cuda:
-            raise RuntimeError("VoxelResBackBone8x needs CUDA tensors (no CPU fallback)")
         n1 = int(coords.shape[0])
-        caps = self._caps(n1, batch_size, worst=False)
-        levels, counts = self._run_fused(feats, coords, batch_size, caps)
-        cnt = counts.tolist()                      # the only host sync of the fused path
-        if any(c >= caps[li] for c, li in zip(cnt[1:], (2, 3, 4, 5))):
-            caps = self._caps(n1, batch_size, worst=True)
-            levels, counts = self._run_fused(feats, coords, batch_size, caps)
-            cnt = counts.tolist()
-        for c, li in zip(cnt[1:], (2, 3, 4, 5)):
-            self._ratios[li] = max(self._ratios.get(li, 0.0), c / max(n1, 1))
-        ns = cnt                                   # cnt[0] = unique level-1 voxels (== n1 for a voxelizer output)
-        outs = []
-        for (x, c, shape), n in zip(levels, ns):
-            outs.append(SparseConvTensor(x[:n], c[:n], shape, batch_size))
-        return tuple(outs)
+        levels, counts, caps = self.fused_async(feats, coords, batch_size)
+        outs = self.fused_finish(levels, counts.tolist(), caps, n1, batch_size)   # the only host sync
+        if outs is None:
+            levels, counts, caps = self.fused_async(feats, coords, batch_size, worst=True)
+            outs = self.fused_finish(levels, counts.tolist(), caps, n1, batch_size)
+        return outs
 
 
 class HeightCompression(nn.Module):

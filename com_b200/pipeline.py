@@ -35,15 +35,32 @@ class FramePipeline:
     @torch.no_grad()
     def forward_device(self, points, frame_offsets):
         """points (N_total, C) fp32 CUDA, frames concatenated; frame_offsets python ints.
-        -> batch_dict with voxel_coords, encoded_spconv_tensor, multi_scale_3d_features, spatial_features."""
+        -> batch_dict with voxel_coords, encoded_spconv_tensor, multi_scale_3d_features, spatial_features.
+        Everything is enqueued without waiting for the device (row counts stay on the device, tensors are
+        capacity-sized); ONE host read of all counts at the end sizes the returned views."""
         batch = len(frame_offsets) - 1
         r = ops.voxelize(points, frame_offsets, self.vsize, self.range, self.T, self.max_voxels, want_voxels=False,
                          mean_dtype=torch.bfloat16, mean_ld=16)
-        m = int(r["counts"][batch].item())
-        bd = {"batch_size": batch, "voxel_features": r["mean"][:m], "voxel_coords": r["coords"][:m],
-              "voxel_num_points": r["num_points"][:m], "voxel_counts": r["counts"]}
-        bd = self.backbone(bd)
-        return self.to_bev(bd)
+        n_dev = r["counts"][batch:batch + 1]
+        worst = False
+        while True:
+            levels, counts, caps = self.backbone.fused_async(r["mean"], r["coords"], batch, n_dev=n_dev, worst=worst)
+            x, c, shape = levels[-1]
+            dense = ops.dense(x, c, batch, shape, n_dev=counts[4:5])
+            host = torch.cat([r["counts"], counts]).tolist()          # the only host synchronisation
+            m, cnt = host[batch], host[batch + 1:]
+            outs = self.backbone.fused_finish(levels, cnt, caps, int(r["coords"].shape[0]), batch)
+            if outs is not None or worst:
+                break
+            worst = True                                              # a learned capacity overflowed: redo
+        x1, x2, x3, x4, out = outs
+        n, ch, d, h, w = dense.shape
+        return {"batch_size": batch, "voxel_features": r["mean"][:m], "voxel_coords": r["coords"][:m],
+                "voxel_num_points": r["num_points"][:m], "voxel_counts": r["counts"],
+                "encoded_spconv_tensor": out, "encoded_spconv_tensor_stride": 8,
+                "multi_scale_3d_features": {"x_conv1": x1, "x_conv2": x2, "x_conv3": x3, "x_conv4": x4},
+                "multi_scale_3d_strides": {"x_conv1": 1, "x_conv2": 2, "x_conv3": 4, "x_conv4": 8},
+                "spatial_features": dense.view(n, ch * d, h, w), "spatial_features_stride": 8}
 
     @torch.no_grad()
     def forward_host(self, frames, pinned=None):

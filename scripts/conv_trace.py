@@ -8,14 +8,35 @@ from com_b200 import _lib, ops
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from util import random_coords
 
-def run(cin, cout, n=300000):
+_real = {}
+
+
+def real_coords():
+    """key-ordered level-1 voxels of 4 synthetic Waymo frames"""
+    if "c" not in _real:
+        from com_b200 import synth
+        fr = [synth.make_frame(seed=1000 + b) for b in range(4)]
+        offs = np.concatenate([[0], np.cumsum([len(f) for f in fr])]).astype(int).tolist()
+        r = ops.voxelize(torch.from_numpy(np.concatenate(fr)).cuda(), offs, synth.VOXEL_SIZE, synth.POINT_CLOUD_RANGE, 5,
+                         150000, want_voxels=False)
+        m = int(r["counts"][4])
+        idx = ops.index_build(r["coords"][:m].contiguous(), 4, [41, 1504, 1504])
+        _real["c"] = (idx.coords[:m].contiguous(), idx)
+    return _real["c"]
+
+
+def run(cin, cout, n=300000, real=False):
     rng = np.random.default_rng(0)
-    shape = [16, 400, 400]
-    coords = random_coords(rng, n, 1, shape)
-    c = coords.astype(np.int64)
-    coords = coords[np.argsort(((c[:, 0] * 16 + c[:, 1]) * 400 + c[:, 2]) * 400 + c[:, 3])]
-    cd = torch.from_numpy(coords).cuda()
-    idx = ops.index_build(cd, 1, shape)
+    if real:
+        cd, idx = real_coords()
+        n = int(cd.shape[0])
+    else:
+        shape = [16, 400, 400]
+        coords = random_coords(rng, n, 1, shape)
+        c = coords.astype(np.int64)
+        coords = coords[np.argsort(((c[:, 0] * 16 + c[:, 1]) * 400 + c[:, 2]) * 400 + c[:, 3])]
+        cd = torch.from_numpy(coords).cuda()
+        idx = ops.index_build(cd, 1, shape)
     nbr = ops.nbrmap_build_indexed(cd, idx, [3, 3, 3], [1, 1, 1], [1, 1, 1], [1, 1, 1])
     x = torch.randn((n, cin), device="cuda").to(torch.bfloat16)
     w = ops.pack_weight_bf16(torch.randn((cout, 27, cin), device="cuda") / 20)
@@ -52,3 +73,5 @@ def run(cin, cout, n=300000):
 
 for cin, cout in ((16, 16), (64, 64), (128, 128)):
     run(cin, cout)
+for cin, cout in ((16, 16), (64, 64)):
+    run(cin, cout, real=True)
