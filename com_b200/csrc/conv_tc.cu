@@ -15,7 +15,7 @@
 // There is no scatter and no atomic: each output row is owned by one CTA and written once with
 // bias / folded BatchNorm / residual / ReLU applied in the epilogue.
 //
-// Warp roles (704 threads, one CTA per SM, persistent over row tiles):
+// Warp roles (768 threads, one CTA per SM, persistent over row tiles):
 //   warps 0-15 producers : neighbour-index tile prefetch (cp.async 4 B, double buffered) and the A gather through
 //                          registers: 2 x LDG.128 (only for neighbours that exist) -> 2 x STS.128 per thread per
 //                          chunk, software-pipelined one chunk deep; a warp instruction covers 32/PPO consecutive
@@ -28,6 +28,7 @@
 //   warp  21   weights   : lane 0 streams the pre-swizzled weight chunk of every stage with cp.async.bulk, or,
 //                          when the whole packed image is <= 64 KB (Cin,Cout <= 32), loads it once and keeps it
 //                          resident.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace comb {
@@ -45,7 +46,8 @@ constexpr int kEpiWarp0 = kProdWarps;      // warps 16..19: (warp & 3) = TMEM la
 constexpr int kMmaWarp = kProdWarps + 4;   // warp 20
 // warp 21 (kProdWarps + 5): weight streamer
 constexpr int kIdxWarp = kProdWarps + 6;   // warp 22: neighbour-index tile prefetcher
-constexpr int kThreadsTC = (kProdWarps + 7) * 32;
+constexpr int kSentinelWarp = kProdWarps + 7;   // warp 23: stage sentinel (barrier wait + proxy fence ahead of the MMA warp)
+constexpr int kThreadsTC = (kProdWarps + 8) * 32;
 constexpr int kPiecesPerThread = (kBM * 8) / kGroupThreads;  // 8 x 16-byte pieces of one A chunk per group thread
 constexpr int kMaxK = 32;         // kernel offsets supported by the index tile
 constexpr int kBResidentMax = 64 * 1024;   // packed weights up to this size stay in shared memory for the whole kernel
@@ -150,13 +152,12 @@ struct TcCfg {
       if (avail / (S * sub_bytes(K)) >= 2 && num_chunks(K) >= S) return S;
     return 1;
   }
-  static __host__ __device__ int stage_bytes(int K) { return subs(K) * sub_bytes(K); }
-  static __host__ __device__ int stages(int K) {
-    int n = (225 * 1024 - fixed_bytes(K)) / stage_bytes(K);
-    const int cap = subs(K) >= 4 ? 2 : (subs(K) == 2 ? 4 : 8);
+  static __host__ __device__ int stages(int K, int S) {
+    int n = (225 * 1024 - fixed_bytes(K)) / (S * sub_bytes(K));
+    const int cap = 8 / S;           // at most 8 chunks in flight
     return n > cap ? cap : n;
   }
-  static size_t smem_bytes(int K) { return (size_t)fixed_bytes(K) + (size_t)stages(K) * stage_bytes(K); }
+  static size_t smem_bytes(int K, int S) { return (size_t)fixed_bytes(K) + (size_t)stages(K, S) * S * sub_bytes(K); }
 };
 
 struct TcParams {
@@ -174,6 +175,7 @@ struct TcParams {
   void* out;
   int out_f32;
   long long* dbg;   // optional trace buffer (comb_debug_conv_trace), NULL in production
+  int S;            // K chunks per pipeline stage (1, 2 or 4), chosen on the host
 };
 
 // trace layout: dbg[(G * 8 + slot)] for G < kDbgChunks, CTA 0 only; slots: 0 mma:full seen, 1 mma:issued+committed,
@@ -187,25 +189,34 @@ __device__ __forceinline__ void dbg_stamp(long long* dbg, int G, int slot) {
   }
 }
 
+__device__ __forceinline__ void dbg_cta_time(long long* dbg, int slot) {   // per-CTA wall clock (ns), slots 0..3
+  if (dbg != nullptr && blockIdx.x < 256) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg[kDbgChunks * 8 + blockIdx.x * 4 + slot] = t;
+  }
+}
+
 constexpr int kMaxStages = 8;
 
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(kThreadsTC, 1) spconv_tc_kernel(TcParams p) {
   using Cfg = TcCfg<CIN, COUT>;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_tfull[2], bar_tempty[2], bar_idx[2],
-      bar_idx_free[2], bar_b;
+  __shared__ uint64_t bar_full[kMaxStages], bar_ready[kMaxStages], bar_empty[kMaxStages], bar_tfull[2], bar_tempty[2],
+      bar_idx[2], bar_idx_free[2], bar_b;
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) dbg_cta_time(p.dbg, 0);
   const int no = eff_n(p.no_max, p.no_dev);
   const int ntiles = (no + kBM - 1) / kBM;
   const int K = p.K;
   const int nchunks = Cfg::num_chunks(K);
   const int kpad = Cfg::k_pad(K);
   const bool bres = Cfg::b_resident(K);
-  const int NS = Cfg::stages(K);
-  const int S = Cfg::subs(K);                       // K chunks per pipeline stage
+  const int S = p.S;                                // K chunks per pipeline stage
+  const int NS = Cfg::stages(K, S);
   const int sub_bytes = Cfg::sub_bytes(K);
   const int stage_bytes = S * sub_bytes;
   const int nstages_tile = (nchunks + S - 1) / S;   // pipeline stages per row tile
@@ -223,6 +234,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) spconv_tc_kernel(TcParams p) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(smem_u32(&bar_full[s]), S * kGroupWarps + (bres ? 0 : 1));
       mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_ready[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bar_tfull[a]), 1);
@@ -248,6 +260,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) spconv_tc_kernel(TcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  if (tid == 0) dbg_cta_time(p.dbg, 1);
 
   if (warp < kProdWarps) {
     // ===================== producers: A gather (global/L2 -> registers -> swizzled shared memory) ==========
@@ -391,13 +404,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) spconv_tc_kernel(TcParams p) {
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + a * COUT;
       for (int st = 0; st < nstages_tile; ++st) {
-        mbar_wait(smem_u32(&bar_full[s]), ph);
+        // the sentinel warp has already waited for the stage and issued the generic->async proxy fence
+        mbar_wait(smem_u32(&bar_ready[s]), ph);
         if (lane == 0) dbg_stamp(p.dbg, (it * nstages_tile + st) * S, 0);
-        // the producers' st.shared (generic proxy) were acquired through the barrier; one proxy fence per stage
-        // makes them visible to the tensor core's async-proxy reads (r1 trace: a fence in every producer thread
-        // cost each gather group ~600 cycles per chunk)
-        fence_proxy_async();
         tc_fence_after();
+        if (lane == 0) dbg_stamp(p.dbg, (it * nstages_tile + st) * S, 6);
         const uint32_t stage_addr = smem_base + s * stage_bytes;
         const int c0 = st * S;
         const int nsub = nchunks - c0 < S ? nchunks - c0 : S;
@@ -417,6 +428,24 @@ __global__ void __launch_bounds__(kThreadsTC, 1) spconv_tc_kernel(TcParams p) {
         }
         __syncwarp();
         if (lane == 0) dbg_stamp(p.dbg, (it * nstages_tile + st) * S, 1);
+        if (++s == NS) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == kSentinelWarp) {
+    // ===================== stage sentinel (warp 23, one lane) =====================
+    // Waits for a stage to be full, makes the producers' st.shared (generic proxy, acquired through the barrier)
+    // visible to the tensor core's async-proxy reads with ONE proxy fence, and hands the stage to the MMA warp.
+    // This keeps barrier-wake-up and fence latency off the MMA warp, whose issue loop bounds the kernel
+    // (r1 trace: ~950 cycles of tcgen05.mma issue per 4-chunk stage + ~600 of wait/fence in between; a fence in
+    // every producer thread instead cost each gather group ~600 cycles per chunk).
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const int total = my_tiles * nstages_tile;
+      for (int g = 0; g < total; ++g) {
+        mbar_wait(smem_u32(&bar_full[s]), ph);
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&bar_ready[s]));
         if (++s == NS) { s = 0; ph ^= 1; }
       }
     }
@@ -470,8 +499,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) spconv_tc_kernel(TcParams p) {
     }
   }
 
+  if (warp == kMmaWarp && lane == 0) dbg_cta_time(p.dbg, 2);
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) dbg_cta_time(p.dbg, 3);
   if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols)
@@ -506,15 +537,28 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
 }
 
 template <int CIN, int COUT>
-int launch_tc(const TcParams& p, cudaStream_t stream) {
+int launch_tc(const TcParams& p_in, cudaStream_t stream) {
   using Cfg = TcCfg<CIN, COUT>;
-  const size_t smem = Cfg::smem_bytes(p.K);
+  TcParams p = p_in;
+  // chunks per stage: COMB_TC_S (tuning knob) or the largest of 4, 2, 1 that still leaves two stages
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("COMB_TC_S");
+    forced = e ? atoi(e) : 0;
+  }
+  p.S = 1;
+  for (int S = (forced == 1 || forced == 2 || forced == 4) ? forced : 4; S > 1; S >>= 1)
+    if (Cfg::stages(p.K, S) >= 2 && Cfg::num_chunks(p.K) >= S) {
+      p.S = S;
+      break;
+    }
+  const size_t smem = Cfg::smem_bytes(p.K, p.S);
   static thread_local bool configured = false;
   if (!configured) {
     COMB_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
     configured = true;
   }
-  if (smem > 227 * 1024 - 2048 || Cfg::stages(p.K) < 2) {
+  if (smem > 227 * 1024 - 2048 || Cfg::stages(p.K, p.S) < 2) {
     set_error("comb_spconv_fwd_bf16: shared memory %zu exceeds the per-CTA limit", smem);
     return COMB_EINVAL;
   }

@@ -41,7 +41,7 @@ def run(cin, cout, n=300000, real=False):
     x = torch.randn((n, cin), device="cuda").to(torch.bfloat16)
     w = ops.pack_weight_bf16(torch.randn((cout, 27, cin), device="cuda") / 20)
     lib = _lib.load()
-    buf = torch.zeros((512 * 8,), dtype=torch.int64, device="cuda")
+    buf = torch.zeros((512 * 8 + 256 * 4,), dtype=torch.int64, device="cuda")
     for _ in range(3):
         ops.spconv_fwd_bf16(x, w, 27, cout, nbr)
     torch.cuda.synchronize()
@@ -50,7 +50,15 @@ def run(cin, cout, n=300000, real=False):
     e0.record(); ops.spconv_fwd_bf16(x, w, 27, cout, nbr); e1.record()
     torch.cuda.synchronize()
     lib.comb_debug_conv_trace(None)
-    t = buf.cpu().numpy().reshape(512, 8)
+    full = buf.cpu().numpy()
+    ct = full[512 * 8:].reshape(256, 4)
+    ct = ct[ct[:, 0] > 0]
+    base = ct[:, 0].min()
+    print('  per-CTA wall clock (us): start min/max %.1f/%.1f, setup done max %.1f, mma done min/median/max %.1f/%.1f/%.1f, exit max %.1f' % (
+        0, (ct[:, 0].max() - base) / 1e3, (ct[:, 1].max() - base) / 1e3, (ct[:, 2].min() - base) / 1e3, float(np.median(ct[:, 2]) - base) / 1e3, (ct[:, 2].max() - base) / 1e3, (ct[:, 3].max() - base) / 1e3))
+    slow = np.argsort(ct[:, 2])[-5:]
+    print('  slowest CTAs (index: mma done us):', [(int(i), round(float(ct[i, 2] - base) / 1e3, 1)) for i in slow], ' CTA0:', round(float(ct[0, 2] - base) / 1e3, 1))
+    t = full[:512 * 8].reshape(512, 8)
     mm = np.nonzero(t[:, 0] > 0)[0]            # chunk slots at which the MMA warp stamped (one per stage)
     S = int(mm[1] - mm[0]) if len(mm) > 1 else 1
     pr = t[:, 2] > 0
@@ -65,13 +73,13 @@ def run(cin, cout, n=300000, real=False):
         print("%4d %11d %11d %11d |%s" % (G, r[2] - t0, r[3] - t0, r[4] - t0, extra))
     iss = t[mm][:, 1]
     print("  mean cycles/stage (mma issue to issue): %.0f  -> %.0f per chunk" % (np.diff(iss).mean(), np.diff(iss).mean() / S))
-    print("  mma: full seen -> issued %.0f cycles" % (t[mm][:, 1] - t[mm][:, 0]).mean())
+    print("  mma: full seen -> issued %.0f cycles (of which proxy fence %.0f); issued -> next full seen %.0f" % (
+        (t[mm][:, 1] - t[mm][:, 0]).mean(), (t[mm][:, 6] - t[mm][:, 0]).mean(), (t[mm][1:, 0] - t[mm][:-1, 1]).mean()))
     print("  prod: loads issued->empty seen %.0f, empty seen->stored+arrived %.0f" % (
         (t[pr][:, 3] - t[pr][:, 2]).mean(), (t[pr][:, 4] - t[pr][:, 3]).mean()))
     epi = t[:, 5][t[:, 5] > 0]
     if len(epi) > 2: print("  epilogue tile-to-tile: %.0f cycles" % np.diff(epi).mean())
 
-for cin, cout in ((16, 16), (64, 64), (128, 128)):
-    run(cin, cout)
+import sys as _s
 for cin, cout in ((16, 16), (64, 64)):
     run(cin, cout, real=True)
