@@ -238,7 +238,7 @@ class VoxelResBackBone8x(nn.Module):
                 contrib *= (kk + ss - 1) // ss
             hard = min(vol, prev * contrib)
             r = self._ratios.get(li)
-            cap = hard if (worst or r is None) else min(hard, int(r * 1.25 * n1) + 1024)
+            cap = hard if (worst or r is None) else min(hard, int(r * 1.5 * n1) + 1024)
             caps[li] = max(cap, 1)
             prev = caps[li]
         return caps

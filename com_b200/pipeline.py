@@ -15,12 +15,12 @@ host synchronisation except one read of the per-level row counts (models.VoxelRe
 import numpy as np
 import torch
 
-from . import models, ops, synth
+from . import _lib, models, ops, synth
 
 
 class FramePipeline:
     def __init__(self, input_channels=5, point_cloud_range=None, voxel_size=None, max_points_per_voxel=5,
-                 max_voxels=150000, device="cuda", seed=0):
+                 max_voxels=150000, device="cuda", seed=0, use_graph=False):
         self.range = list(point_cloud_range or synth.POINT_CLOUD_RANGE)
         self.vsize = list(voxel_size or synth.VOXEL_SIZE)
         self.T, self.max_voxels, self.C = int(max_points_per_voxel), int(max_voxels), int(input_channels)
@@ -31,6 +31,38 @@ class FramePipeline:
         self.backbone = models.VoxelResBackBone8x(None, input_channels, self.grid_size).to(device).eval()
         self.to_bev = models.HeightCompression(None)
         self.device = torch.device(device)
+        self.use_graph = bool(use_graph)     # replay the step as one CUDA graph (see _forward_graph)
+        self._graph = None
+        self.graph_launches = 0              # kernels launched through graph replays (bench.py's gpu_launches)
+
+    # ------------------------------------------------------------------ enqueue (no host synchronisation)
+    def _enqueue(self, points, offsets, batch, worst=False):
+        """Enqueue voxelize -> backbone -> dense on the current stream.  `offsets`: python ints or a device int32
+        tensor (batch+1).  Returns capacity-sized tensors and ONE device tensor holding every row count."""
+        r = ops.voxelize(points, offsets, self.vsize, self.range, self.T, self.max_voxels, want_voxels=False,
+                         mean_dtype=torch.bfloat16, mean_ld=16)
+        n_dev = r["counts"][batch:batch + 1]
+        levels, counts, caps = self.backbone.fused_async(r["mean"], r["coords"], batch, n_dev=n_dev, worst=worst)
+        x, c, shape = levels[-1]
+        dense = ops.dense(x, c, batch, shape, n_dev=counts[4:5])
+        return dict(r=r, levels=levels, caps=caps, dense=dense, all_counts=torch.cat([r["counts"], counts]))
+
+    def _finish(self, q, batch):
+        """One host read of all row counts, then exact-size views (None when a learned capacity overflowed)."""
+        host = q["all_counts"].tolist()                              # the only host synchronisation
+        m, cnt = host[batch], host[batch + 1:]
+        r = q["r"]
+        outs = self.backbone.fused_finish(q["levels"], cnt, q["caps"], int(r["coords"].shape[0]), batch)
+        if outs is None:
+            return None
+        x1, x2, x3, x4, out = outs
+        n, ch, d, h, w = q["dense"].shape
+        return {"batch_size": batch, "voxel_features": r["mean"][:m], "voxel_coords": r["coords"][:m],
+                "voxel_num_points": r["num_points"][:m], "voxel_counts": r["counts"],
+                "encoded_spconv_tensor": out, "encoded_spconv_tensor_stride": 8,
+                "multi_scale_3d_features": {"x_conv1": x1, "x_conv2": x2, "x_conv3": x3, "x_conv4": x4},
+                "multi_scale_3d_strides": {"x_conv1": 1, "x_conv2": 2, "x_conv3": 4, "x_conv4": 8},
+                "spatial_features": q["dense"].view(n, ch * d, h, w), "spatial_features_stride": 8}
 
     @torch.no_grad()
     def forward_device(self, points, frame_offsets):
@@ -39,28 +71,57 @@ class FramePipeline:
         Everything is enqueued without waiting for the device (row counts stay on the device, tensors are
         capacity-sized); ONE host read of all counts at the end sizes the returned views."""
         batch = len(frame_offsets) - 1
-        r = ops.voxelize(points, frame_offsets, self.vsize, self.range, self.T, self.max_voxels, want_voxels=False,
-                         mean_dtype=torch.bfloat16, mean_ld=16)
-        n_dev = r["counts"][batch:batch + 1]
-        worst = False
-        while True:
-            levels, counts, caps = self.backbone.fused_async(r["mean"], r["coords"], batch, n_dev=n_dev, worst=worst)
-            x, c, shape = levels[-1]
-            dense = ops.dense(x, c, batch, shape, n_dev=counts[4:5])
-            host = torch.cat([r["counts"], counts]).tolist()          # the only host synchronisation
-            m, cnt = host[batch], host[batch + 1:]
-            outs = self.backbone.fused_finish(levels, cnt, caps, int(r["coords"].shape[0]), batch)
-            if outs is not None or worst:
-                break
-            worst = True                                              # a learned capacity overflowed: redo
-        x1, x2, x3, x4, out = outs
-        n, ch, d, h, w = dense.shape
-        return {"batch_size": batch, "voxel_features": r["mean"][:m], "voxel_coords": r["coords"][:m],
-                "voxel_num_points": r["num_points"][:m], "voxel_counts": r["counts"],
-                "encoded_spconv_tensor": out, "encoded_spconv_tensor_stride": 8,
-                "multi_scale_3d_features": {"x_conv1": x1, "x_conv2": x2, "x_conv3": x3, "x_conv4": x4},
-                "multi_scale_3d_strides": {"x_conv1": 1, "x_conv2": 2, "x_conv3": 4, "x_conv4": 8},
-                "spatial_features": dense.view(n, ch * d, h, w), "spatial_features_stride": 8}
+        if self.use_graph:
+            return self._forward_graph(points, frame_offsets, batch)
+        out = self._finish(self._enqueue(points, frame_offsets, batch), batch)
+        if out is None:                                              # a learned capacity overflowed: redo
+            out = self._finish(self._enqueue(points, frame_offsets, batch, worst=True), batch)
+        return out
+
+    # ------------------------------------------------------------------ CUDA-graph replay
+    def _forward_graph(self, points, frame_offsets, batch):
+        """The whole step as ONE cudaGraphLaunch: the kernels read frame offsets and row counts from device
+        memory, so the captured launch sequence is valid for any frames that fit the captured capacities
+        (point capacity, voxel capacity, learned level capacities).  Host work per step: two small copies into
+        the static input buffers, the launch, one read of the counts."""
+        n = int(points.shape[0])
+        g = self._graph
+        if g is None or g["batch"] != batch or n > g["n_cap"]:
+            g = self._capture(points.to(self.device, non_blocking=True), frame_offsets, batch)
+        g["points"][:n].copy_(points, non_blocking=True)             # D2D, or H2D straight from pinned memory
+        g["offs_host"][: batch + 1] = torch.tensor(frame_offsets, dtype=torch.int32)
+        g["offs"].copy_(g["offs_host"], non_blocking=True)
+        g["graph"].replay()
+        self.graph_launches += g["launches"]
+        out = self._finish(g["q"], batch)
+        if out is None:                                              # capacity overflow: eager redo + recapture later
+            self._graph = None
+            out = self._finish(self._enqueue(points, frame_offsets, batch, worst=True), batch)
+        return out
+
+    def _capture(self, points, frame_offsets, batch):
+        n = int(points.shape[0])
+        n_cap = max((int(n * 1.25) + 65535) // 65536 * 65536, 65536)
+        # eager warm-up: builds the weight plan, sets kernel attributes, learns the level capacities
+        for _ in range(2):
+            if self._finish(self._enqueue(points, frame_offsets, batch), batch) is None:
+                self._finish(self._enqueue(points, frame_offsets, batch, worst=True), batch)
+        g = {"batch": batch, "n_cap": n_cap,
+             "points": torch.zeros((n_cap, int(points.shape[1])), dtype=torch.float32, device=points.device),
+             "offs": torch.zeros((batch + 1,), dtype=torch.int32, device=points.device),
+             "offs_host": torch.zeros((batch + 1,), dtype=torch.int32).pin_memory()}
+        g["points"][:n].copy_(points)
+        g["offs"].copy_(torch.tensor(frame_offsets, dtype=torch.int32))
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        lib = _lib.load()
+        n0 = lib.comb_launch_count()
+        with torch.cuda.graph(graph):
+            g["q"] = self._enqueue(g["points"], g["offs"], batch)
+        g["launches"] = int(lib.comb_launch_count() - n0)    # kernels of this library inside one replay
+        g["graph"] = graph
+        self._graph = g
+        return g
 
     @torch.no_grad()
     def forward_host(self, frames, pinned=None):
@@ -71,5 +132,7 @@ class FramePipeline:
         else:
             offs = np.concatenate([[0], np.cumsum([len(f) for f in frames])]).astype(int).tolist()
             host = torch.from_numpy(np.concatenate(frames, axis=0))
+        if self.use_graph:
+            return self._forward_graph(host, offs, len(offs) - 1)    # H2D goes straight into the graph's input buffer
         dev = host.to(self.device, non_blocking=True)
         return self.forward_device(dev, offs)

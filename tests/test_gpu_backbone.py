@@ -154,3 +154,24 @@ def test_waymo_shape_batch_properties():
     # a frame's result does not depend on what else is in the batch (shardability):
     # key order puts frame 0 first
     assert torch.equal(x1.features[:n0], f0["multi_scale_3d_features"]["x_conv1"].features)
+
+
+def test_graph_replay_matches_eager():
+    """The whole step replayed as one CUDA graph gives the bits of the eager path, for the captured batch and
+    for a different batch (other point counts, other voxel counts) that fits the captured capacities."""
+    fa = [synth.make_small_cloud(n, seed=s, extent=(25.0, 25.0, 4.0)) for s, n in ((1, 30000), (2, 22000))]
+    fb = [synth.make_small_cloud(n, seed=s, extent=(25.0, 25.0, 4.0)) for s, n in ((3, 18000), (4, 27000))]
+    for f in fa + fb:
+        f[:, 2] *= 0.4
+    eager = pipeline.FramePipeline(point_cloud_range=RANGE, voxel_size=VSIZE, max_voxels=40000, seed=3)
+    graph = pipeline.FramePipeline(point_cloud_range=RANGE, voxel_size=VSIZE, max_voxels=40000, seed=3, use_graph=True)
+    for frames in (fa, fb, fa):
+        e = eager.forward_host(frames)
+        g = graph.forward_host(frames)
+        assert torch.equal(e["voxel_coords"], g["voxel_coords"])
+        assert torch.equal(e["encoded_spconv_tensor"].indices, g["encoded_spconv_tensor"].indices)
+        assert torch.equal(e["encoded_spconv_tensor"].features, g["encoded_spconv_tensor"].features)
+        assert torch.equal(e["spatial_features"], g["spatial_features"])
+        for n in ("x_conv1", "x_conv2", "x_conv3", "x_conv4"):
+            assert torch.equal(e["multi_scale_3d_features"][n].features, g["multi_scale_3d_features"][n].features)
+    assert graph._graph is not None

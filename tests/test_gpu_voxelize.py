@@ -123,3 +123,19 @@ def test_idempotent_and_deterministic():
     n = int(a["counts"][1])
     for k in ("voxels", "coords", "num_points"):
         assert torch.equal(a[k][:n], b[k][:n])
+
+
+def test_device_side_frame_offsets():
+    """Frame offsets read from device memory (CUDA-graph friendly launch sequence): same bits as host offsets,
+    also when the point buffer is larger than the frames it holds."""
+    frames = [synth.make_small_cloud(n, seed=40 + i) for i, n in enumerate([4000, 0, 1500, 9000])]
+    offs = np.concatenate([[0], np.cumsum([len(f) for f in frames])]).astype(np.int32)
+    pts = np.concatenate(frames)
+    padded = np.concatenate([pts, np.full((3000, 5), 0.123, np.float32)])      # stale rows beyond off[batch]
+    a = ops.voxelize(torch.from_numpy(pts).cuda(), offs.tolist(), SMALL_VS, SMALL_RANGE, 5, 600, mean_dtype=torch.float32)
+    b = ops.voxelize(torch.from_numpy(padded).cuda(), torch.from_numpy(offs).cuda(), SMALL_VS, SMALL_RANGE, 5, 600,
+                     mean_dtype=torch.float32)
+    assert torch.equal(a["counts"], b["counts"])
+    n = int(a["counts"][-1])
+    for k in ("voxels", "coords", "num_points", "mean"):
+        assert torch.equal(a[k][:n], b[k][:n])
