@@ -46,6 +46,18 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
+def load_traffic():
+    """dram bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/conv_traffic.json, written by scripts/ncu_traffic.py from the .ncu-rep), or None."""
+    p = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
 def make_frames(seeds):
     from com_b200 import synth
     cache = os.path.join("/tmp", "comb200_frames")
@@ -309,6 +321,10 @@ def ours(args):
     evs_p = []
     for _ in range(args.steps):
         flush.fill_(1)
+        # the eager step costs more host time (58 ctypes launches + events) than device time: park the stream behind
+        # a ~4 ms spin so that every launch of the step is already queued when the first kernel starts, and the
+        # per-family events bracket back-to-back kernel execution instead of host launch gaps
+        torch.cuda._sleep(8_000_000)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         step_eager()
@@ -374,10 +390,12 @@ def ours(args):
         conv = fam.get("spconv_fwd_bf16", dict(ms=1e-9, flops=0, bytes=0, launches=1))
         conv_s = conv["ms"] / 1e3
         tf = conv["flops"] / conv_s / 1e12
-        roof = {"bound": "tensor", "kernel": "spconv_tc_kernel (tcgen05 gather-GEMM, 21 launches/step)",
+        conv_impl = "spconv_tc_kernel (A in shared memory)" if os.environ.get("COMB_CONV_IMPL", "ts")[:2] == "ss" \
+            else "spconv_ts_kernel (A gathered into tensor memory)"
+        roof = {"bound": "tensor", "kernel": "%s: tcgen05 gather-GEMM, 21 launches/step" % conv_impl,
                 "achieved": tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": tf / peaks["tf_sust"],
                 "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks["src"],
-                "traffic": None,
+                "traffic": load_traffic(),
                 "share_of_step": conv_s / t_prof,
                 "hbm_view": {"achieved": conv["bytes"] / conv_s / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                              "frac": conv["bytes"] / conv_s / 1e9 / peaks["hbm"]},

@@ -1,0 +1,32 @@
+// Internal interface between the C-ABI entry points of the bf16 sparse convolution (conv_tc.cu) and its two
+// tcgen05 implementations: "ts" (A operand gathered into tensor memory, conv_ts.cu — the default) and "ss"
+// (A operand gathered into shared memory, conv_tc.cu — kept for A/B measurements, COMB_CONV_IMPL=ss).
+// The packed weight image differs between the two (the ts form permutes K inside a chunk), so the choice is
+// made once per process and used by both comb_spconv_pack_weight_bf16 and comb_spconv_fwd_bf16.
+#pragma once
+#include "common.cuh"
+
+namespace comb {
+
+struct ConvFwdArgs {
+  const __nv_bfloat16* in;
+  const uint8_t* wpacked;
+  const int* nbr;
+  int ld, no_max;
+  const int* no_dev;
+  int K;
+  int epi;
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  void* out;
+  int out_f32;
+  long long* dbg;   // optional trace buffer (comb_debug_conv_trace), NULL in production
+};
+
+int ts_fwd_bf16(const ConvFwdArgs& p, int Cin_p, int Cout, cudaStream_t stream);
+int ts_pack_weight(const float* weight, int Cout, int K, int Cin, int Cin_p, int nchunks, void* wpacked,
+                   cudaStream_t stream);
+
+}  // namespace comb

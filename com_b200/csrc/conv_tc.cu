@@ -30,6 +30,8 @@
 //                          resident.
 #include <stdlib.h>
 #include "common.cuh"
+#include "conv_impl.cuh"
+#include "tc_util.cuh"
 
 namespace comb {
 namespace {
@@ -52,79 +54,8 @@ constexpr int kPiecesPerThread = (kBM * 8) / kGroupThreads;  // 8 x 16-byte piec
 constexpr int kMaxK = 32;         // kernel offsets supported by the index tile
 constexpr int kBResidentMax = 64 * 1024;   // packed weights up to this size stay in shared memory for the whole kernel
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace tcu;
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// Warp-uniform leader election: unlike `lane == 0` the compiler knows the predicate is uniform, so tcgen05
-// operands stay in uniform registers (the per-lane form costs a serialised R2UR loop per instruction).
-__device__ __forceinline__ bool elect_one_sync() {
-  uint32_t pred;
-  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between
-// 8-row groups | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-         (2ull << 61);
-}
 
 template <int CIN, int COUT>
 struct TcCfg {
@@ -587,6 +518,16 @@ static int chunks_for(int Cin_p, int K) {
   return Cin_p <= 64 ? (K + 64 / Cin_p - 1) / (64 / Cin_p) : K * (Cin_p / 64);
 }
 
+// COMB_CONV_IMPL=ss selects the shared-memory-A kernel of this file; the default is the tensor-memory-A kernel.
+static bool use_ts() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("COMB_CONV_IMPL");
+    v = (e && e[0] == 's' && e[1] == 's') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 }  // namespace
 }  // namespace comb
 
@@ -611,6 +552,7 @@ extern "C" int comb_spconv_pack_weight_bf16(const float* weight, int Cout, int K
   COMB_CHECK_ARG(Cin >= 1 && Cin <= Cin_p, "comb_spconv_pack_weight_bf16: Cin %d > padded %d", Cin, Cin_p);
   COMB_CHECK_ARG(Cout % 8 == 0 && Cout >= 8 && K >= 1, "comb_spconv_pack_weight_bf16: bad Cout/K");
   const int nchunks = chunks_for(Cin_p, K);
+  if (use_ts()) return ts_pack_weight(weight, Cout, K, Cin, Cin_p, nchunks, wpacked, stream);
   const long long total = (long long)nchunks * Cout * kChunkK;
   const int grid = cdiv(total, 256);
   __nv_bfloat16* out = (__nv_bfloat16*)wpacked;
@@ -638,7 +580,25 @@ extern "C" int comb_spconv_fwd_bf16(const void* in_feats, int Cin_p, const void*
   COMB_CHECK_ARG(out_dtype == COMB_DT_F32 || out_dtype == COMB_DT_BF16, "comb_spconv_fwd_bf16: bad out dtype");
   if (no_max == 0) return COMB_OK;
   COMB_CHECK_ARG(in_feats && wpacked && nbr && out, "comb_spconv_fwd_bf16: null pointer");
-  COMB_CHECK_ARG((ld % 1) == 0, "comb_spconv_fwd_bf16: ld");
+  if (use_ts()) {
+    ConvFwdArgs a;
+    a.in = (const __nv_bfloat16*)in_feats;
+    a.wpacked = (const uint8_t*)wpacked;
+    a.nbr = nbr;
+    a.ld = ld;
+    a.no_max = no_max;
+    a.no_dev = no_dev;
+    a.K = K;
+    a.epi = epi_flags;
+    a.bias = bias;
+    a.scale = scale;
+    a.shift = shift;
+    a.residual = (const __nv_bfloat16*)residual;
+    a.out = out;
+    a.out_f32 = out_dtype == COMB_DT_F32;
+    a.dbg = g_conv_trace;
+    return ts_fwd_bf16(a, Cin_p, Cout, stream);
+  }
   TcParams p;
   p.in = (const __nv_bfloat16*)in_feats;
   p.wpacked = (const uint8_t*)wpacked;

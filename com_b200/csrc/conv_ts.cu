@@ -1,0 +1,574 @@
+// a7 — sparse convolution forward on tcgen05 with the gathered A operand staged in TENSOR MEMORY (TS form).
+//
+// Replaces the gather-GEMM-scatter of spconv's SubMConv3d / SparseConv3d forward
+// (pcdet/models/backbones_3d/spconv_backbone.py:191-232).  Same output-stationary implicit GEMM as conv_tc.cu
+//
+//   D[128 rows, Cout] (TMEM, fp32)  +=  A_chunk[128, 64] (TMEM, bf16)  x  B_chunk[Cout, 64]^T (smem, bf16)
+//
+// but the gathered rows never touch shared memory: the gather warps load neighbour rows from global/L2 into
+// registers (LDG.128, only for neighbours that exist) and write them straight into TMEM with tcgen05.st, and
+// the MMA reads A from TMEM (tcgen05.mma [d], [a], b-desc).  r1 trace of the SS kernel: every tcgen05.mma
+// (M=128,K=16) cost >= 57 cycles at issue whatever N was, because the 4 KB A operand was fetched through the
+// shared-memory port that the 16 KB/chunk of gather stores also went through; with A in TMEM the instruction
+// floor is 128*N/256 cycles and the shared-memory port only carries the weights.
+//
+// TMEM map (512 columns): [0,256) accumulators (256/Cout buffers, ring), [256,512) eight A chunk slots of 32
+// columns (= 64 bf16 per row).  A row m of a tile lives in TMEM lane m; a warp may only touch lanes
+// 32*(warp%4)..+31, so gather warp w serves row quarter w%4 and chunk slots G with G%4 == w/4.
+//
+// K permutation.  tcgen05.st.16x256b hands thread t of a warp columns 8g+2(t%4)+{0,1} of rows t/4 and t/4+8
+// (g = repeat).  To keep the global loads 16 bytes per lane and 64 contiguous bytes per 4 lanes, the thread's
+// 16-byte piece p = 4*half + (t%4) of the 128-byte chunk row goes to column groups 2*half and 2*half+1.  So the
+// source element e = 8p + w of a chunk sits at K position  kappa(e) = 32*half + 16*(w/4) + 4*(t%4) + (w%4);
+// the weight image is packed with the same permutation (ts_pack_weight), so the contraction is unchanged.
+//
+// Streamed weights (images that do not fit in shared memory: 64x64, 64x128, 128x128) are consumed by TWO row
+// tiles per stage (a CTA walks 256-row super-tiles), which halves the L2->SM weight traffic that bounded those
+// layers (one 128-row tile re-read the full 216-864 KB image).
+//
+// Warp roles (768 threads, one CTA per SM, persistent over super-tiles):
+//   warps 0-15  gather    : index LDS -> predicated LDG.128 -> tcgen05.st -> wait::st -> arrive on the slot
+//   warps 16-19 epilogue  : tcgen05.ld -> bias / BN affine / residual / ReLU -> 16-byte stores
+//   warp  20    MMA       : elected lane issues 4 x tcgen05.mma (K=16) per chunk, commits slot / weight stage / tile
+//   warp  21    weights   : resident image (one bulk copy) or a ring of per-chunk stages (cp.async.bulk)
+//   warp  22    indices   : neighbour-index tiles (27 x 128 ints), 2*T buffers, 16-byte cp.async
+#include <stdlib.h>
+#include "common.cuh"
+#include "conv_impl.cuh"
+#include "tc_util.cuh"
+
+namespace comb {
+namespace {
+
+using namespace tcu;
+
+constexpr int kBM = 128;
+constexpr int kChunkK = 64;
+constexpr int kGatherWarps = 16;
+constexpr int kEpiWarp0 = 16;
+constexpr int kMmaWarp = 20;
+constexpr int kBWarp = 21;
+constexpr int kIdxWarp = 22;
+constexpr int kThreads = 24 * 32;
+constexpr int kMaxK = 32;
+constexpr int kMaxBStages = 8;
+constexpr int kSmemBudget = 225 * 1024;
+constexpr int kBResidentMax = 160 * 1024;
+
+template <int CIN, int COUT>
+struct TsCfg {
+  static constexpr int kOffPerChunk = CIN <= 64 ? 64 / CIN : 1;
+  static constexpr int kChunksPerOff = CIN <= 64 ? 1 : CIN / 64;
+  static constexpr int kBBytes = COUT * 128;
+  static __host__ __device__ int num_chunks(int K) {
+    return CIN <= 64 ? (K + kOffPerChunk - 1) / kOffPerChunk : K * kChunksPerOff;
+  }
+  static __host__ __device__ int k_pad(int K) { return CIN <= 64 ? num_chunks(K) * kOffPerChunk : K; }
+  static __host__ __device__ bool b_resident(int K) { return num_chunks(K) * kBBytes <= kBResidentMax; }
+  static __host__ __device__ int tiles_per_pass(int K) { return b_resident(K) ? 1 : 2; }   // T
+  // TMEM: accumulator ring in [0, d_cols), A stages of 128 columns (4 chunks) behind it
+  static __host__ __device__ int d_cols(int K) { return (tiles_per_pass(K) == 2 || COUT == 128) ? 256 : 128; }
+  static __host__ __device__ int n_acc(int K) {
+    const int n = d_cols(K) / COUT;
+    return n > 4 ? 4 : n;
+  }
+  static __host__ __device__ int a_stages(int K) { return (512 - d_cols(K)) / 128; }   // 2 or 3
+  static __host__ __device__ int idx_bytes(int K) { return 2 * tiles_per_pass(K) * k_pad(K) * kBM * 4; }
+  static __host__ __device__ int b_stages(int K) {   // streamed weights: ring of 2-chunk stages
+    int n = (kSmemBudget - 2048 - idx_bytes(K)) / (2 * kBBytes);
+    return n > kMaxBStages ? kMaxBStages : n;
+  }
+  static size_t smem_bytes(int K) {
+    return 2048 + (size_t)idx_bytes(K) +
+           (b_resident(K) ? (size_t)num_chunks(K) * kBBytes : (size_t)b_stages(K) * 2 * kBBytes);
+  }
+};
+
+// barrier block at the start of the (1024-byte aligned) dynamic shared memory: 32-bit shared addresses are plain
+// arithmetic on one base register (taking the address of a static __shared__ array costs an S2R + LEA every time)
+constexpr uint32_t kBarFull = 0, kBarEmpty = 32, kBarBFull = 64, kBarBEmpty = 128, kBarTFull = 192, kBarTEmpty = 256,
+                   kBarIdx = 320, kBarIdxFree = 352, kBarB = 384, kTmemSlot = 392;
+
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint4& a0, const uint4& b0, const uint4& a1,
+                                                   const uint4& b1) {
+  // a = row t/4, b = row t/4 + 8; 0/1 = first / second 16-byte piece of the thread (see the K permutation above)
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(a0.x), "r"(a0.y), "r"(b0.x), "r"(b0.y), "r"(a0.z), "r"(a0.w), "r"(b0.z), "r"(b0.w), "r"(a1.x), "r"(a1.y),
+      "r"(b1.x), "r"(b1.y), "r"(a1.z), "r"(a1.w), "r"(b1.z), "r"(b1.w)
+      : "memory");
+}
+// trace layout: dbg[G*16 + slot] for chunk slot G < 512 of CTA 0.  slots: 0 mma saw the
+// chunk full, 1 mma issued + committed, 2 gather (row quarter 0 of the owning group) start, 3 gather saw the slot
+// empty (loads issued before), 4 gather stored + arrived, 5 epilogue finished tile G, 6 mma loop top, 7 gather saw idx
+constexpr int kDbgChunks = 512;
+__device__ __forceinline__ void dbg_stamp(long long* dbg, int G, int slot) {
+  if (dbg != nullptr && blockIdx.x == 0 && G < kDbgChunks) {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    dbg[G * 16 + slot] = t;
+  }
+}
+__device__ __forceinline__ void dbg_cta_time(long long* dbg, int slot) {   // per-CTA wall clock (ns), slots 0..3
+  if (dbg != nullptr && blockIdx.x < 256) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg[kDbgChunks * 16 + blockIdx.x * 4 + slot] = t;
+  }
+}
+
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
+  using Cfg = TsCfg<CIN, COUT>;
+  extern __shared__ uint8_t smem_raw[];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) dbg_cta_time(p.dbg, 0);
+  const int no = eff_n(p.no_max, p.no_dev);
+  const int ntiles = (no + kBM - 1) / kBM;
+  const int K = p.K;
+  const int nchunks = Cfg::num_chunks(K);
+  const int kpad = Cfg::k_pad(K);
+  const bool bres = Cfg::b_resident(K);
+  const int T = bres ? 1 : 2, lT = bres ? 0 : 1;     // row tiles per pass (super-tile = T*128 rows)
+  const int NI = 2 * T;                              // index-tile buffers
+  const int NB = Cfg::b_stages(K);
+  const int ND = Cfg::n_acc(K);                      // accumulator ring (power of two, >= T)
+  const int NS = Cfg::a_stages(K);                   // A stages of 4 chunks
+  const uint32_t colA = (uint32_t)Cfg::d_cols(K);
+  const int nsuper = (ntiles + T - 1) >> lT;
+  const int my_super = nsuper > (int)blockIdx.x ? (nsuper - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int CT = nchunks << lT;                      // chunk slots per super-tile, order (c, t)
+  const int nst = (CT + 3) >> 2;                     // stages per super-tile (the last one may be partial)
+
+  // shared memory map (1024-byte aligned): [barriers 1 KB] [weights: resident image | NB streamed 2-chunk stages]
+  // [index tiles NI x kpad x 128]
+  const uint32_t bars = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = bars + 1024u;
+  const uint32_t idx_base = w_base + (bres ? nchunks * Cfg::kBBytes : NB * 2 * Cfg::kBBytes);
+  const uint32_t idx_buf_bytes = (uint32_t)kpad * kBM * 4;
+
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(bars + kBarFull + 8 * s, kGatherWarps);
+      mbar_init(bars + kBarEmpty + 8 * s, 1);
+      mbar_init(bars + kBarIdx + 8 * s, 32);
+      mbar_init(bars + kBarIdxFree + 8 * s, kGatherWarps);
+    }
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(bars + kBarBFull + 8 * s, 1);
+      mbar_init(bars + kBarBEmpty + 8 * s, 1);
+      mbar_init(bars + kBarTFull + 8 * s, 1);
+      mbar_init(bars + kBarTEmpty + 8 * s, 4);
+    }
+    mbar_init(bars + kBarB, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + kTmemSlot), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // index-tile rows of the padding offsets (k in [K, kpad)) stay -1 for the whole kernel
+  for (int e = tid; e < NI * (kpad - K) * kBM; e += kThreads) {
+    const int buf = e / ((kpad - K) * kBM), r = e - buf * (kpad - K) * kBM;
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(idx_base + buf * idx_buf_bytes + (K * kBM + r) * 4), "r"(-1) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bars + kTmemSlot) : "memory");
+  if (tid == 0) dbg_cta_time(p.dbg, 1);
+
+  if (warp < kGatherWarps) {
+    // ===================== gather: global/L2 -> registers -> TMEM =====================
+    // group g (4 warps, one per row quarter) fills chunk sub-slot g of every stage
+    const int q = warp & 3, grp = warp >> 2;
+    const int j = lane & 3, r8 = lane >> 2;
+    // this thread's two 16-byte pieces of the 128-byte chunk row: p0 = j (bytes 16j..), p1 = 4 + j (bytes 64+16j..)
+    int slot0, slot1, eo0, eo1;      // kernel-offset slot inside the chunk and element offset inside the feature row
+    if (CIN <= 64) {
+      slot0 = (8 * j) / CIN;
+      eo0 = (8 * j) % CIN;
+      slot1 = (32 + 8 * j) / CIN;
+      eo1 = (32 + 8 * j) % CIN;
+    } else {
+      slot0 = slot1 = 0;
+      eo0 = 8 * j;
+      eo1 = 32 + 8 * j;
+    }
+    const __nv_bfloat16* in = p.in;
+    const bool tr = q == 0 && grp == 0 && lane == 0;
+    int s = 0, gst = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < my_super; ++it) {
+      for (int st = 0; st < nst; ++st, ++gst) {
+        const int x = st * 4 + grp;
+        const bool have = x < CT;
+        uint4 v[2][2][2];     // [16-lane half][row, row+8][piece]
+        if (tr) dbg_stamp(p.dbg, gst, 2);
+        if (have) {
+          const int c = x >> lT, t = x & (T - 1);
+          const int n = (it << lT) + t;                  // tile sequence number of this CTA
+          const int buf = n & (NI - 1);
+          mbar_wait(bars + kBarIdx + 8 * buf, (uint32_t)(n >> (lT + 1)) & 1u);
+          if (tr) dbg_stamp(p.dbg, gst, 7);
+          const uint32_t idx_c = idx_base + (uint32_t)buf * idx_buf_bytes +
+                                 (uint32_t)(CIN <= 64 ? c * Cfg::kOffPerChunk : c / Cfg::kChunksPerOff) * kBM * 4;
+          const int ehalf = CIN > 64 ? (c % Cfg::kChunksPerOff) * 64 : 0;
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const int row = q * 32 + h * 16 + rr * 8 + r8;
+              int rw0, rw1;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw0) : "r"(idx_c + (uint32_t)(slot0 * kBM + row) * 4) : "memory");
+              if (CIN <= 32) {
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw1) : "r"(idx_c + (uint32_t)(slot1 * kBM + row) * 4) : "memory");
+              } else {
+                rw1 = rw0;
+              }
+              v[h][rr][0] = make_uint4(0u, 0u, 0u, 0u);
+              v[h][rr][1] = make_uint4(0u, 0u, 0u, 0u);
+              if (rw0 >= 0) v[h][rr][0] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)(uint32_t)rw0 * CIN + ehalf + eo0));
+              if (rw1 >= 0) v[h][rr][1] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)(uint32_t)rw1 * CIN + ehalf + eo1));
+            }
+        }
+        mbar_wait(bars + kBarEmpty + 8 * s, ph ^ 1u);
+        if (tr) dbg_stamp(p.dbg, gst, 3);
+        if (have) {
+          tc_fence_after();
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + colA + (uint32_t)((s * 4 + grp) * 32);
+          tmem_st_16x256b_x4(ta, v[0][0][0], v[0][1][0], v[0][0][1], v[0][1][1]);
+          tmem_st_16x256b_x4(ta + (16u << 16), v[1][0][0], v[1][1][0], v[1][0][1], v[1][1][1]);
+          tmem_st_wait();
+          tc_fence_before();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + kBarFull + 8 * s);
+        if (tr) dbg_stamp(p.dbg, gst, 4);
+        if (++s == NS) { s = 0; ph ^= 1u; }
+      }
+      // all index reads of this super-tile are consumed: hand its buffers back
+      __syncwarp();
+      if (lane == 0)
+        for (int t = 0; t < T; ++t) mbar_arrive(bars + kBarIdxFree + 8 * (((it << lT) + t) & (NI - 1)));
+    }
+  } else if (warp < kEpiWarp0 + 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int ntile_seq = my_super << lT;
+    for (int n = 0; n < ntile_seq; ++n) {
+      const int tile = (((int)blockIdx.x + (n >> lT) * (int)gridDim.x) << lT) + (n & (T - 1));
+      const int a = n & (ND - 1);
+      const int row = tile * kBM + q * 32 + lane;
+      const bool live = row < no;
+      uint4 rv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * COUT);
+      if ((p.epi & COMB_EPI_RESIDUAL) && live) {   // issued before the accumulator is ready
+        rv[0] = __ldg(rp);
+        rv[1] = __ldg(rp + 1);
+      }
+      mbar_wait(bars + kBarTFull + 8 * a, (uint32_t)(n / ND) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * COUT;
+#pragma unroll
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        uint4 rn[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (c0 + 16 < COUT && (p.epi & COMB_EPI_RESIDUAL) && live) {
+          rn[0] = __ldg(rp + (c0 + 16) / 8);
+          rn[1] = __ldg(rp + (c0 + 16) / 8 + 1);
+        }
+        tmem_ld_wait();
+        if (live) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.epi & COMB_EPI_BIAS) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + c0 + i);
+          }
+          if (p.epi & COMB_EPI_AFFINE) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaf(f[i], __ldg(p.scale + c0 + i), __ldg(p.shift + c0 + i));
+          }
+          if (p.epi & COMB_EPI_RESIDUAL) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv[h]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float2 tt = __bfloat1622float2(r2[i]);
+                f[h * 8 + 2 * i] += tt.x;
+                f[h * 8 + 2 * i + 1] += tt.y;
+              }
+            }
+          }
+          if (p.epi & COMB_EPI_RELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
+          }
+          if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * COUT + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * COUT + c0);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint4 o;
+              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(f[h * 8 + 2 * i], f[h * 8 + 2 * i + 1]);
+              op[h] = o;
+            }
+          }
+        }
+        rv[0] = rn[0];
+        rv[1] = rn[1];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + kBarTEmpty + 8 * a);
+      if (warp == kEpiWarp0 && lane == 0) dbg_stamp(p.dbg, n, 5);
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer =====================
+    // One barrier round per STAGE of 4 chunks (r1 trace: with one round per chunk this warp's own loop — waits,
+    // fence, operand set-up, 4 UTCHMMA, commits: ~110 SASS instructions — took ~600 cycles per chunk and bounded
+    // every layer while the gather ran 8 chunks ahead).
+    // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B, N>>3 [17,23), M>>4 [24,29)
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    // The whole loop runs in ONE elected thread (no per-stage WARPSYNC / ELECT / reconvergence).  A barrier check costs
+    // ~100 cycles even when the phase has long completed and the tcgen05.mma queue is shallow, so the readiness of the
+    // NEXT stage is probed (mbarrier.test_wait, non-blocking) in the middle of issuing the current one: in steady state
+    // the tensor pipe never drains while this thread looks at barriers.
+    if (elect_one_sync()) {
+      int s = 0, bs = 0, it = 0, st = 0;
+      uint32_t ph = 0, bph = 0;
+      bool ready = false;
+      if (bres) mbar_wait(bars + kBarB, 0);
+      const int total = my_super * nst;
+      for (int gst = 0; gst < total; ++gst) {
+        const int n0 = it << lT;
+        dbg_stamp(p.dbg, gst, 6);
+        if (!ready) {
+          if (st == 0)
+            for (int t = 0; t < T; ++t) {
+              const int n = n0 + t;
+              mbar_wait(bars + kBarTEmpty + 8 * (n & (ND - 1)), ((uint32_t)(n / ND) & 1u) ^ 1u);
+            }
+          if (!bres) mbar_wait(bars + kBarBFull + 8 * bs, bph);
+          mbar_wait(bars + kBarFull + 8 * s, ph);
+        }
+        dbg_stamp(p.dbg, gst, 0);
+        tc_fence_after();
+        // ring positions of the next stage
+        const int s2 = s + 1 == NS ? 0 : s + 1;
+        const uint32_t ph2 = s + 1 == NS ? ph ^ 1u : ph;
+        const int bs2 = bs + 1 == NB ? 0 : bs + 1;
+        const uint32_t bph2 = bs + 1 == NB ? bph ^ 1u : bph;
+        const bool last_st = st == nst - 1;
+        const int x0 = st * 4;
+        // issue order: the 4 K-slices of one chunk back to back (r1 measurement: interleaving chunks / accumulators
+        // between consecutive MMAs made every MMA ~45 % slower, 109 vs 75 cycles, at every N)
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+          const int x = x0 + sub;
+          if (x < CT) {
+            const int c = x >> lT, t = x & (T - 1);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(((n0 + t) & (ND - 1)) * COUT);
+            const uint32_t tmem_a = tmem_base + colA + (uint32_t)((s * 4 + sub) * 32);
+            const uint64_t bdesc = make_desc_sw128(w_base + (uint32_t)(bres ? c : bs * 2 + (c & 1)) * Cfg::kBBytes);
+#pragma unroll
+            for (int kk = 0; kk < kChunkK / 16; ++kk)
+              umma_bf16_ts(tmem_d, tmem_a + 8 * kk, bdesc + 2 * kk, idesc, (c | kk) != 0 ? 1u : 0u);
+          }
+          if (sub == 1) {   // probe the next stage while the second half of this one is still to be issued
+            ready = gst + 1 < total && mbar_test(bars + kBarFull + 8 * s2, ph2);
+            if (!bres) ready = ready && mbar_test(bars + kBarBFull + 8 * bs2, bph2);
+            if (last_st)
+              for (int t = 0; t < T; ++t) {
+                const int n = n0 + T + t;
+                ready = ready && mbar_test(bars + kBarTEmpty + 8 * (n & (ND - 1)), ((uint32_t)(n / ND) & 1u) ^ 1u);
+              }
+          }
+        }
+        umma_commit(bars + kBarEmpty + 8 * s);
+        if (!bres) umma_commit(bars + kBarBEmpty + 8 * bs);
+        if (last_st)
+          for (int t = 0; t < T; ++t) umma_commit(bars + kBarTFull + 8 * ((n0 + t) & (ND - 1)));
+        dbg_stamp(p.dbg, gst, 1);
+        s = s2;
+        ph = ph2;
+        if (!bres) { bs = bs2; bph = bph2; }
+        if (last_st) { st = 0; ++it; } else { ++st; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kIdxWarp) {
+    // ===================== neighbour-index prefetcher =====================
+    // idx[buf][k][r] = nbr[k][tile*128 + r] (-1 beyond the last row), NI buffers ahead of the gather warps.
+    const bool vec_ok = (p.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.nbr) & 15) == 0);
+    const int ntile_seq = my_super << lT;
+    for (int n = 0; n < ntile_seq; ++n) {
+      const int buf = n & (NI - 1);
+      const int use = n >> (lT + 1);       // how many times this buffer has been filled before
+      if (use > 0) mbar_wait(bars + kBarIdxFree + 8 * buf, (uint32_t)(use - 1) & 1u);
+      const int tile = (((int)blockIdx.x + (n >> lT) * (int)gridDim.x) << lT) + (n & (T - 1));
+      const int row0 = tile * kBM + lane * 4;   // this lane: 4 consecutive rows
+      const uint32_t dst = idx_base + (uint32_t)buf * idx_buf_bytes + lane * 16;
+      if (vec_ok && row0 + 3 < no) {
+        for (int k = 0; k < K; ++k)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + k * kBM * 4),
+                       "l"(p.nbr + (size_t)k * p.ld + row0)
+                       : "memory");
+      } else {
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            if (row0 + qq < no)
+              cp_async4(dst + k * kBM * 4 + qq * 4, p.nbr + (size_t)k * p.ld + row0 + qq);
+            else
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + k * kBM * 4 + qq * 4), "r"(-1) : "memory");
+          }
+      }
+      cp_async_mbar_arrive_noinc(bars + kBarIdx + 8 * buf);
+    }
+  } else if (warp == kBWarp && lane == 0) {
+    // ===================== weights =====================
+    if (bres) {
+      const uint32_t bytes = (uint32_t)nchunks * Cfg::kBBytes;
+      mbar_arrive_expect_tx(bars + kBarB, bytes);
+      bulk_copy_g2s(w_base, p.wpacked, bytes, bars + kBarB);
+    } else {
+      // one 2-chunk weight stage per A stage (T = 2: a stage is chunks 2*st, 2*st+1 for both row tiles)
+      int bs = 0;
+      uint32_t bph = 0;
+      for (int it = 0; it < my_super; ++it)
+        for (int st = 0; st < nst; ++st) {
+          const int c0 = 2 * st;
+          const uint32_t bytes = (uint32_t)(nchunks - c0 < 2 ? nchunks - c0 : 2) * Cfg::kBBytes;
+          mbar_wait(bars + kBarBEmpty + 8 * bs, bph ^ 1u);
+          mbar_arrive_expect_tx(bars + kBarBFull + 8 * bs, bytes);
+          bulk_copy_g2s(w_base + bs * 2 * Cfg::kBBytes, p.wpacked + (size_t)c0 * Cfg::kBBytes, bytes, bars + kBarBFull + 8 * bs);
+          if (++bs == NB) { bs = 0; bph ^= 1u; }
+        }
+    }
+  }
+
+  if (warp == kMmaWarp && lane == 0) dbg_cta_time(p.dbg, 2);
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) dbg_cta_time(p.dbg, 3);
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// Weight image: chunk c, output channel n, K position kappa (see the permutation above) -> W[n][k][ci], in the
+// K-major SWIZZLE_128B layout the B descriptor expects.
+template <int CIN>
+__global__ void __launch_bounds__(256) ts_pack_kernel(const float* __restrict__ w, int Cout, int K, int Cin_real,
+                                                       int nchunks, __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)nchunks * Cout * kChunkK;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kappa = (int)(i % kChunkK);
+    const int n = (int)((i / kChunkK) % Cout);
+    const int c = (int)(i / ((long long)kChunkK * Cout));
+    const int half = kappa >> 5, wq = (kappa >> 4) & 1, j = (kappa >> 2) & 3, wl = kappa & 3;
+    const int e = 8 * (4 * half + j) + 4 * wq + wl;        // source element of the chunk row
+    int k, ci;
+    if constexpr (CIN <= 64) {
+      k = c * (64 / CIN) + e / CIN;
+      ci = e % CIN;
+    } else {
+      k = c / (CIN / 64);
+      ci = (c % (CIN / 64)) * 64 + e;
+    }
+    float v = 0.0f;
+    if (k < K && ci < Cin_real) v = w[((size_t)n * K + k) * Cin_real + ci];
+    const int qq = kappa >> 3, within = kappa & 7;
+    const size_t byte_off = (size_t)c * Cout * 128 + (size_t)(n >> 3) * 1024 + (n & 7) * 128 + ((qq ^ (n & 7)) << 4) + within * 2;
+    out[byte_off / 2] = __float2bfloat16(v);
+  }
+}
+
+template <int CIN, int COUT>
+int launch_ts(const ConvFwdArgs& p, cudaStream_t stream) {
+  using Cfg = TsCfg<CIN, COUT>;
+  const size_t smem = Cfg::smem_bytes(p.K);
+  static thread_local bool configured = false;
+  if (!configured) {
+    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    configured = true;
+  }
+  if (smem > 227 * 1024 - 1024 || (!Cfg::b_resident(p.K) && Cfg::b_stages(p.K) < 2)) {
+    set_error("comb_spconv_fwd_bf16: shared memory %zu exceeds the per-CTA limit", smem);
+    return COMB_EINVAL;
+  }
+  const int T = Cfg::tiles_per_pass(p.K);
+  const int nsuper = cdiv(cdiv(p.no_max, kBM), T);
+  const int grid = nsuper < sm_count() ? nsuper : sm_count();
+  spconv_ts_kernel<CIN, COUT><<<grid, kThreads, smem, stream>>>(p);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}
+
+template <int CIN>
+int dispatch_cout(int Cout, const ConvFwdArgs& p, cudaStream_t stream) {
+  switch (Cout) {
+    case 16: return launch_ts<CIN, 16>(p, stream);
+    case 32: return launch_ts<CIN, 32>(p, stream);
+    case 64: return launch_ts<CIN, 64>(p, stream);
+    case 128: return launch_ts<CIN, 128>(p, stream);
+  }
+  set_error("comb_spconv_fwd_bf16: Cout %d not in {16,32,64,128}", Cout);
+  return COMB_EINVAL;
+}
+
+}  // namespace
+
+int ts_fwd_bf16(const ConvFwdArgs& p, int Cin_p, int Cout, cudaStream_t stream) {
+  COMB_CHECK_ARG(p.K >= 1 && p.K <= kMaxK, "comb_spconv_fwd_bf16: K %d outside [1,%d]", p.K, kMaxK);
+  switch (Cin_p) {
+    case 16: return dispatch_cout<16>(Cout, p, stream);
+    case 32: return dispatch_cout<32>(Cout, p, stream);
+    case 64: return dispatch_cout<64>(Cout, p, stream);
+    case 128: return dispatch_cout<128>(Cout, p, stream);
+  }
+  set_error("comb_spconv_fwd_bf16: Cin_p %d not in {16,32,64,128}", Cin_p);
+  return COMB_EINVAL;
+}
+
+int ts_pack_weight(const float* weight, int Cout, int K, int Cin, int Cin_p, int nchunks, void* wpacked,
+                   cudaStream_t stream) {
+  const long long total = (long long)nchunks * Cout * kChunkK;
+  const int grid = cdiv(total, 256);
+  __nv_bfloat16* out = (__nv_bfloat16*)wpacked;
+  switch (Cin_p) {
+    case 16: ts_pack_kernel<16><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, out); break;
+    case 32: ts_pack_kernel<32><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, out); break;
+    case 64: ts_pack_kernel<64><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, out); break;
+    case 128: ts_pack_kernel<128><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, out); break;
+    default: COMB_CHECK_ARG(false, "comb_spconv_pack_weight_bf16: Cin_p %d not in {16,32,64,128}", Cin_p);
+  }
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}
+
+}  // namespace comb

@@ -80,6 +80,6 @@ def run(cin, cout, n=300000, real=False):
     epi = t[:, 5][t[:, 5] > 0]
     if len(epi) > 2: print("  epilogue tile-to-tile: %.0f cycles" % np.diff(epi).mean())
 
-import sys as _s
-for cin, cout in ((16, 16), (64, 64)):
-    run(cin, cout, real=True)
+if __name__ == "__main__":
+    for cin, cout in ((16, 16), (64, 64)):
+        run(cin, cout, real=True)

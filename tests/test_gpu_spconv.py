@@ -115,16 +115,18 @@ def test_fwd_bf16_epilogue_and_device_count():
     assert (got[no - 77:] == -7.0).all()                # rows beyond the device-side count are untouched
 
 
-def test_bf16_many_tiles_persistent_loop():
-    """More tiles than SMs: every CTA walks several tiles (pipeline phases wrap, TMEM double buffer)."""
-    rng = np.random.default_rng(12)
-    coords = random_coords(rng, 50000, 4, [16, 96, 96])
+@pytest.mark.parametrize("C,n", [(16, 50000), (32, 50000), (64, 90000), (128, 90000)])
+def test_bf16_many_tiles_persistent_loop(C, n):
+    """More (super-)tiles than SMs: every CTA walks several of them (slot / weight-stage / accumulator / index
+    rings wrap; streamed weights at C >= 64 use 256-row super-tiles, odd tile counts leave a half-empty one)."""
+    rng = np.random.default_rng(12 + C)
+    coords = random_coords(rng, n, 4, [16, 96, 96])
     nbr = oracle.subm_nbrmap(coords, [16, 96, 96])
-    feats = rng.normal(size=(len(coords), 16)).astype(np.float32)
-    W = (rng.normal(size=(16, 27, 16)) / 20).astype(np.float32)
-    assert nbr.shape[1] > 148 * 128 * 2 and (nbr >= 0).mean() > 0.08
-    want = oracle.conv_fwd(bf16_round(feats), bf16_round(W), nbr)
-    got = ops.spconv_fwd_bf16(ops.cast_pad(cuda(feats), 16), ops.pack_weight_bf16(cuda(W)), 27, 16, cuda(nbr),
+    feats = rng.normal(size=(len(coords), C)).astype(np.float32)
+    W = (rng.normal(size=(C, 27, C)) / np.sqrt(27 * C)).astype(np.float32)
+    assert nbr.shape[1] > 148 * 128 * (2 if C < 64 else 4) and (nbr >= 0).mean() > 0.08
+    want = oracle.fast_conv_fwd(bf16_round(feats), bf16_round(W), nbr)
+    got = ops.spconv_fwd_bf16(ops.cast_pad(cuda(feats), C), ops.pack_weight_bf16(cuda(W)), 27, C, cuda(nbr),
                               out_dtype=torch.float32).cpu().numpy()
     assert rel_err(got, want) < 1e-4
 
