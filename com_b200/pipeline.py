@@ -136,3 +136,107 @@ class FramePipeline:
             return self._forward_graph(host, offs, len(offs) - 1)    # H2D goes straight into the graph's input buffer
         dev = host.to(self.device, non_blocking=True)
         return self.forward_device(dev, offs)
+
+
+class FrameStream:
+    """Double-buffered streaming front end of one FramePipeline in CUDA-graph mode — the serving loop:
+
+        ticket = stream.submit(pinned_points, frame_offsets)      # returns at once
+        ...                                                       # submit the next batch before collecting
+        res = stream.result(ticket)                               # pinned host views of the encoded tensor
+
+    The H2D copy of batch k+1 (copy-in stream) and the D2H copy of the result of batch k-1 (copy-out stream)
+    overlap the kernels of batch k (launch stream); the three streams are ordered with events only, the host blocks
+    in result() alone.  Replaces the synchronous load_data_to_gpu -> model -> .cpu() loop of
+    pcdet/models/__init__.py:23-37 and tools/eval_utils/eval_utils.py:58-71 for this path.
+    Result views stay valid until the second submit() after their own."""
+
+    def __init__(self, pipe, host_points, frame_offsets):
+        if not pipe.use_graph:
+            raise RuntimeError("FrameStream needs a FramePipeline(use_graph=True)")
+        self.pipe, dev = pipe, pipe.device
+        self.batch = len(frame_offsets) - 1
+        g = pipe._graph
+        if g is None or g["batch"] != self.batch or int(host_points.shape[0]) > g["n_cap"]:
+            g = pipe._capture(host_points.to(dev), frame_offsets, self.batch)
+        self.g = g
+        q = g["q"]
+        x, c, _ = q["levels"][-1]
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        self.slots = []
+        for _ in range(2):
+            self.slots.append(dict(
+                in_pts=torch.empty_like(g["points"]), in_offs=torch.empty_like(g["offs"]),
+                offs_host=torch.zeros((self.batch + 1,), dtype=torch.int32).pin_memory(),
+                out_feat=torch.empty_like(x), out_idx=torch.empty_like(c), out_cnt=torch.empty_like(q["all_counts"]),
+                h_feat=torch.empty(tuple(x.shape), dtype=x.dtype).pin_memory(),
+                h_idx=torch.empty(tuple(c.shape), dtype=c.dtype).pin_memory(),
+                h_cnt=torch.empty(tuple(q["all_counts"].shape), dtype=q["all_counts"].dtype).pin_memory(),
+                ev_in=ev(), ev_in_free=ev(), ev_out=ev(), ev_done=ev(), src=None))
+        self.k = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = int(x.numel() * x.element_size() + c.numel() * c.element_size() +
+                             q["all_counts"].numel() * q["all_counts"].element_size())
+
+    @torch.no_grad()
+    def submit(self, host_points, frame_offsets):
+        g, slot = self.g, self.slots[self.k % 2]
+        n = int(host_points.shape[0])
+        if len(frame_offsets) - 1 != self.batch or n > g["n_cap"]:
+            raise RuntimeError("FrameStream: batch shape differs from the captured one (build a new stream)")
+        main = torch.cuda.current_stream(self.pipe.device)
+        slot["ev_in"].synchronize()                       # the previous H2D out of offs_host has long finished
+        slot["offs_host"][:] = torch.tensor(frame_offsets, dtype=torch.int32)
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(slot["ev_in_free"])      # the launch stream has consumed the slot's previous input
+            slot["in_pts"][:n].copy_(host_points, non_blocking=True)
+            slot["in_offs"].copy_(slot["offs_host"], non_blocking=True)
+            slot["ev_in"].record(self.s_in)
+        main.wait_event(slot["ev_in"])
+        g["points"][:n].copy_(slot["in_pts"][:n], non_blocking=True)
+        g["offs"].copy_(slot["in_offs"], non_blocking=True)
+        slot["ev_in_free"].record(main)
+        g["graph"].replay()
+        self.pipe.graph_launches += g["launches"]
+        q = g["q"]
+        x, c, _ = q["levels"][-1]
+        main.wait_event(slot["ev_done"])                  # the slot's previous result has left the device
+        slot["out_feat"].copy_(x, non_blocking=True)
+        slot["out_idx"].copy_(c, non_blocking=True)
+        slot["out_cnt"].copy_(q["all_counts"], non_blocking=True)
+        slot["ev_out"].record(main)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(slot["ev_out"])
+            slot["h_feat"].copy_(slot["out_feat"], non_blocking=True)
+            slot["h_idx"].copy_(slot["out_idx"], non_blocking=True)
+            slot["h_cnt"].copy_(slot["out_cnt"], non_blocking=True)
+            slot["ev_done"].record(self.s_out)
+        slot["src"] = (host_points, list(frame_offsets))
+        self.h2d_bytes = n * int(host_points.shape[1]) * 4 + (self.batch + 1) * 4
+        self.k += 1
+        return self.k - 1
+
+    def done_event(self, ticket):
+        return self.slots[ticket % 2]["ev_done"]
+
+    @torch.no_grad()
+    def result(self, ticket):
+        slot, batch = self.slots[ticket % 2], self.batch
+        slot["ev_done"].synchronize()
+        cnt = slot["h_cnt"].tolist()
+        lv = cnt[batch + 1:]
+        caps = self.g["q"]["caps"]
+        n1 = int(self.g["q"]["r"]["coords"].shape[0])
+        hard = self.pipe.backbone._caps(n1, batch, worst=True)
+        if any(c >= caps[li] and caps[li] < hard[li] for c, li in zip(lv[1:], (2, 3, 4, 5))):
+            # a learned level capacity overflowed: redo this batch synchronously with worst-case capacities
+            host, offs = slot["src"]
+            self.pipe._graph = None
+            bd = self.pipe.forward_host(None, pinned=(host, offs))
+            enc = bd["encoded_spconv_tensor"]
+            return {"features": enc.features.cpu(), "indices": enc.indices.cpu(),
+                    "voxel_counts": bd["voxel_counts"].cpu(), "rows": int(enc.features.shape[0])}
+        n = lv[4]
+        return {"features": slot["h_feat"][:n], "indices": slot["h_idx"][:n], "voxel_counts": slot["h_cnt"][: batch + 1],
+                "rows": n}

@@ -175,3 +175,36 @@ def test_graph_replay_matches_eager():
         for n in ("x_conv1", "x_conv2", "x_conv3", "x_conv4"):
             assert torch.equal(e["multi_scale_3d_features"][n].features, g["multi_scale_3d_features"][n].features)
     assert graph._graph is not None
+
+
+def test_frame_stream_matches_synchronous_path():
+    """FrameStream (double-buffered H2D / kernels / D2H on three streams) returns, for every batch of an interleaved
+    sequence, the bits of the synchronous path — results are collected one submit late, as in the serving loop."""
+    def mk(seeds_sizes):
+        fr = [synth.make_small_cloud(n, seed=s, extent=(25.0, 25.0, 4.0)) for s, n in seeds_sizes]
+        for f in fr:
+            f[:, 2] *= 0.4
+        offs = np.concatenate([[0], np.cumsum([len(f) for f in fr])]).astype(int).tolist()
+        return torch.from_numpy(np.concatenate(fr, axis=0)).pin_memory(), offs, fr
+    batches = [mk(((1, 30000), (2, 22000))), mk(((3, 18000), (4, 27000))), mk(((5, 25000), (6, 25000)))]
+    eager = pipeline.FramePipeline(point_cloud_range=RANGE, voxel_size=VSIZE, max_voxels=40000, seed=3)
+    graph = pipeline.FramePipeline(point_cloud_range=RANGE, voxel_size=VSIZE, max_voxels=40000, seed=3, use_graph=True)
+    want = []
+    for host, offs, fr in batches:
+        e = eager.forward_host(fr)["encoded_spconv_tensor"]
+        want.append((e.features.cpu(), e.indices.cpu()))
+    stream = pipeline.FrameStream(graph, batches[0][0], batches[0][1])
+    order = [0, 1, 2, 1, 0, 2, 2]
+    prev, got = None, []
+    for b in order:
+        tk = stream.submit(batches[b][0], batches[b][1])
+        if prev is not None:
+            r = stream.result(prev[0])
+            got.append((prev[1], r["features"].clone(), r["indices"].clone(), r["rows"]))
+        prev = (tk, b)
+    r = stream.result(prev[0])
+    got.append((prev[1], r["features"].clone(), r["indices"].clone(), r["rows"]))
+    assert [g[0] for g in got] == order
+    for b, f, i, n in got:
+        assert n == want[b][0].shape[0]
+        assert torch.equal(f, want[b][0]) and torch.equal(i, want[b][1])

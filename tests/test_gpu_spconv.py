@@ -79,7 +79,7 @@ def bf16_round(a):
     return torch.from_numpy(a).to(torch.bfloat16).float().numpy()
 
 
-@pytest.mark.parametrize("Cin,Cout", [(5, 16), (16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128)])
+@pytest.mark.parametrize("Cin,Cout", [(5, 16), (16, 16), (16, 32), (32, 16), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128)])
 @pytest.mark.parametrize("subm", [True, False])
 def test_fwd_bf16_tensor_core(Cin, Cout, subm):
     coords, out_coords, nbr, feats, W, rng = make_case(Cin * 17 + Cout, 3000, Cin, Cout, st=(1, 1, 1) if subm else (2, 2, 2), subm=subm)
