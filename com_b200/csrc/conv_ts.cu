@@ -146,7 +146,23 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   const int ND = Cfg::n_acc(K);                      // accumulator ring (power of two, >= T)
   const int NS = Cfg::a_stages(K);                   // A stages of 4 chunks
   const uint32_t colA = (uint32_t)Cfg::d_cols(K);
-  const int nsuper = (ntiles + T - 1) >> lT;
+  // Passes.  A pass walks T row tiles; with T = 2 the last wave of passes is split into single-tile passes when
+  // that shortens it (r <= grid/2 leftover super-tiles become 2r half passes on 2r CTAs: the absent second tile
+  // is neither gathered nor multiplied).
+  int nsuper = (ntiles + T - 1) >> lT, nfull = nsuper;
+  {
+    const int r = nsuper % (int)gridDim.x;
+    if (T == 2 && r > 0 && 2 * r <= (int)gridDim.x) {
+      nfull = nsuper - r;
+      nsuper = nfull + (ntiles - 2 * nfull);
+    }
+  }
+  // row tile of tile-sequence number n of this CTA (a tile index past the end reads as "no rows")
+  auto tile_of = [&](int n) -> int {
+    const int sidx = (int)blockIdx.x + (n >> lT) * (int)gridDim.x;
+    if (sidx < nfull) return (sidx << lT) + (n & (T - 1));
+    return (n & (T - 1)) == 0 ? (nfull << lT) + (sidx - nfull) : 0x00FFFFFF;
+  };
   const int my_super = nsuper > (int)blockIdx.x ? (nsuper - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int CT = nchunks << lT;                      // chunk slots per super-tile, order (c, t)
   const int nst = (CT + 3) >> 2;                     // stages per super-tile (the last one may be partial)
@@ -215,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
     for (int it = 0; it < my_super; ++it) {
       for (int st = 0; st < nst; ++st, ++gst) {
         const int x = st * 4 + grp;
-        const bool have = x < CT;
+        const bool have = x < CT && !((x & (T - 1)) == 1 && (int)blockIdx.x + it * (int)gridDim.x >= nfull);
         uint4 v[2][2][2];     // [16-lane half][row, row+8][piece]
         if (tr) dbg_stamp(p.dbg, gst, 2);
         if (have) {
@@ -255,7 +271,6 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
           tmem_st_wait();
           tc_fence_before();
         }
-        __syncwarp();
         if (lane == 0) mbar_arrive(bars + kBarFull + 8 * s);
         if (tr) dbg_stamp(p.dbg, gst, 4);
         if (++s == NS) { s = 0; ph ^= 1u; }
@@ -270,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
     const int q = warp & 3;
     const int ntile_seq = my_super << lT;
     for (int n = 0; n < ntile_seq; ++n) {
-      const int tile = (((int)blockIdx.x + (n >> lT) * (int)gridDim.x) << lT) + (n & (T - 1));
+      const int tile = tile_of(n);
       const int a = n & (ND - 1);
       const int row = tile * kBM + q * 32 + lane;
       const bool live = row < no;
@@ -383,6 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
         const uint32_t bph2 = bs + 1 == NB ? bph ^ 1u : bph;
         const bool last_st = st == nst - 1;
         const int x0 = st * 4;
+        const bool t1_absent = (int)blockIdx.x + it * (int)gridDim.x >= nfull;   // single-tile pass of the split last wave
         // issue order: the 4 K-slices of one chunk back to back (r1 measurement: interleaving chunks / accumulators
         // between consecutive MMAs made every MMA ~45 % slower, 109 vs 75 cycles, at every N)
 #pragma unroll
@@ -393,9 +409,11 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
             const uint32_t tmem_d = tmem_base + (uint32_t)(((n0 + t) & (ND - 1)) * COUT);
             const uint32_t tmem_a = tmem_base + colA + (uint32_t)((s * 4 + sub) * 32);
             const uint64_t bdesc = make_desc_sw128(w_base + (uint32_t)(bres ? c : bs * 2 + (c & 1)) * Cfg::kBBytes);
+            if (!(t == 1 && t1_absent)) {     // the absent second tile of a half pass has nothing to multiply
 #pragma unroll
-            for (int kk = 0; kk < kChunkK / 16; ++kk)
-              umma_bf16_ts(tmem_d, tmem_a + 8 * kk, bdesc + 2 * kk, idesc, (c | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < kChunkK / 16; ++kk)
+                umma_bf16_ts(tmem_d, tmem_a + 8 * kk, bdesc + 2 * kk, idesc, (c | kk) != 0 ? 1u : 0u);
+            }
           }
           if (sub == 1) {   // probe the next stage while the second half of this one is still to be issued
             ready = gst + 1 < total && mbar_test(bars + kBarFull + 8 * s2, ph2);
@@ -428,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       const int buf = n & (NI - 1);
       const int use = n >> (lT + 1);       // how many times this buffer has been filled before
       if (use > 0) mbar_wait(bars + kBarIdxFree + 8 * buf, (uint32_t)(use - 1) & 1u);
-      const int tile = (((int)blockIdx.x + (n >> lT) * (int)gridDim.x) << lT) + (n & (T - 1));
+      const int tile = tile_of(n);
       const int row0 = tile * kBM + lane * 4;   // this lane: 4 consecutive rows
       const uint32_t dst = idx_base + (uint32_t)buf * idx_buf_bytes + lane * 16;
       if (vec_ok && row0 + 3 < no) {
