@@ -46,7 +46,8 @@ constexpr int kBM = 128;
 constexpr int kChunkK = 64;
 constexpr int kGatherWarps = 16;
 constexpr int kEpiWarp0 = 16;
-constexpr int kMmaWarp = 20;
+constexpr int kMmaWarp = 20;       // issues the MMAs of row tile 0 of every pass (and owns the TMEM allocation)
+constexpr int kMmaWarp2 = 23;      // issues the MMAs of row tile 1
 constexpr int kBWarp = 21;
 constexpr int kIdxWarp = 22;
 constexpr int kThreads = 24 * 32;
@@ -65,15 +66,22 @@ struct TsCfg {
   }
   static __host__ __device__ int k_pad(int K) { return CIN <= 64 ? num_chunks(K) * kOffPerChunk : K; }
   static __host__ __device__ bool b_resident(int K) { return num_chunks(K) * kBBytes <= kBResidentMax; }
-  static __host__ __device__ int tiles_per_pass(int K) { return b_resident(K) ? 1 : 2; }   // T
+  static __host__ __device__ int tiles_per_pass(int) { return 2; }   // T: every pass walks two row tiles, one per MMA-issuing thread
   // TMEM: accumulator ring in [0, d_cols), A stages of 128 columns (4 chunks) behind it
-  static __host__ __device__ int d_cols(int K) { return (tiles_per_pass(K) == 2 || COUT == 128) ? 256 : 128; }
+  static __host__ __device__ int d_cols(int) { return COUT >= 64 ? 256 : 128; }
   static __host__ __device__ int n_acc(int K) {
     const int n = d_cols(K) / COUT;
     return n > 4 ? 4 : n;
   }
   static __host__ __device__ int a_stages(int K) { return (512 - d_cols(K)) / 128; }   // 2 or 3
-  static __host__ __device__ int idx_bytes(int K) { return 2 * tiles_per_pass(K) * k_pad(K) * kBM * 4; }
+  // index-tile ring: 8 buffers (4 passes ahead of the gather) when shared memory allows, else 4.  (r1 ncu source
+  // view: with 2 buffers the gather warps' most executed instructions were the spin on the index barrier.)
+  static __host__ __device__ int n_idx(int K) {
+    const int big = 2048 + 8 * k_pad(K) * kBM * 4;
+    if (b_resident(K)) return num_chunks(K) * kBBytes + big <= kSmemBudget ? 8 : 4;
+    return (kSmemBudget - big) / (2 * kBBytes) >= 4 ? 8 : 4;
+  }
+  static __host__ __device__ int idx_bytes(int K) { return n_idx(K) * k_pad(K) * kBM * 4; }
   static __host__ __device__ int b_stages(int K) {   // streamed weights: ring of 2-chunk stages
     int n = (kSmemBudget - 2048 - idx_bytes(K)) / (2 * kBBytes);
     return n > kMaxBStages ? kMaxBStages : n;
@@ -87,7 +95,7 @@ struct TsCfg {
 // barrier block at the start of the (1024-byte aligned) dynamic shared memory: 32-bit shared addresses are plain
 // arithmetic on one base register (taking the address of a static __shared__ array costs an S2R + LEA every time)
 constexpr uint32_t kBarFull = 0, kBarEmpty = 32, kBarBFull = 64, kBarBEmpty = 128, kBarTFull = 192, kBarTEmpty = 256,
-                   kBarIdx = 320, kBarIdxFree = 352, kBarB = 384, kTmemSlot = 392;
+                   kBarIdx = 320, kBarIdxFree = 384, kBarB = 448, kTmemSlot = 456;
 
 __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint4& a0, const uint4& b0, const uint4& a1,
                                                    const uint4& b1) {
@@ -127,21 +135,22 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   using Cfg = TsCfg<CIN, COUT>;
   extern __shared__ uint8_t smem_raw[];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) dbg_cta_time(p.dbg, 0);
+  if (TRACE && tid == 0) dbg_cta_time(p.dbg, 0);
   const int no = eff_n(p.no_max, p.no_dev);
   const int ntiles = (no + kBM - 1) / kBM;
   const int K = p.K;
   const int nchunks = Cfg::num_chunks(K);
   const int kpad = Cfg::k_pad(K);
   const bool bres = Cfg::b_resident(K);
-  const int T = bres ? 1 : 2, lT = bres ? 0 : 1;     // row tiles per pass (super-tile = T*128 rows)
-  const int NI = 2 * T;                              // index-tile buffers
+  constexpr int T = 2, lT = 1;                       // row tiles per pass (256 rows): one per MMA-issuing thread
+  const int NI = Cfg::n_idx(K);                      // index-tile buffers (8 or 4)
+  const int lNI = NI == 8 ? 3 : 2;
   const int NB = Cfg::b_stages(K);
   const int ND = Cfg::n_acc(K);                      // accumulator ring (power of two, >= T)
   const int NS = Cfg::a_stages(K);                   // A stages of 4 chunks
@@ -177,15 +186,15 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) {
       mbar_init(bars + kBarFull + 8 * s, kGatherWarps);
-      mbar_init(bars + kBarEmpty + 8 * s, 1);
-      mbar_init(bars + kBarIdx + 8 * s, 32);
-      mbar_init(bars + kBarIdxFree + 8 * s, kGatherWarps);
+      mbar_init(bars + kBarEmpty + 8 * s, 2);          // both MMA threads commit
     }
     for (int s = 0; s < 8; ++s) {
       mbar_init(bars + kBarBFull + 8 * s, 1);
-      mbar_init(bars + kBarBEmpty + 8 * s, 1);
+      mbar_init(bars + kBarBEmpty + 8 * s, 2);
       mbar_init(bars + kBarTFull + 8 * s, 1);
       mbar_init(bars + kBarTEmpty + 8 * s, 4);
+      mbar_init(bars + kBarIdx + 8 * s, 32);
+      mbar_init(bars + kBarIdxFree + 8 * s, kGatherWarps);
     }
     mbar_init(bars + kBarB, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -205,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bars + kTmemSlot) : "memory");
-  if (tid == 0) dbg_cta_time(p.dbg, 1);
+  if (TRACE && tid == 0) dbg_cta_time(p.dbg, 1);
 
   if (warp < kGatherWarps) {
     // ===================== gather: global/L2 -> registers -> TMEM =====================
@@ -233,13 +242,13 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
         const int x = st * 4 + grp;
         const bool have = x < CT && !((x & (T - 1)) == 1 && (int)blockIdx.x + it * (int)gridDim.x >= nfull);
         uint4 v[2][2][2];     // [16-lane half][row, row+8][piece]
-        if (tr) dbg_stamp(p.dbg, gst, 2);
+        if (TRACE && tr) dbg_stamp(p.dbg, gst, 2);
         if (have) {
           const int c = x >> lT, t = x & (T - 1);
           const int n = (it << lT) + t;                  // tile sequence number of this CTA
           const int buf = n & (NI - 1);
-          mbar_wait(bars + kBarIdx + 8 * buf, (uint32_t)(n >> (lT + 1)) & 1u);
-          if (tr) dbg_stamp(p.dbg, gst, 7);
+          mbar_wait_sleep(bars + kBarIdx + 8 * buf, (uint32_t)(n >> lNI) & 1u);
+          if (TRACE && tr) dbg_stamp(p.dbg, gst, 7);
           const uint32_t idx_c = idx_base + (uint32_t)buf * idx_buf_bytes +
                                  (uint32_t)(CIN <= 64 ? c * Cfg::kOffPerChunk : c / Cfg::kChunksPerOff) * kBM * 4;
           const int ehalf = CIN > 64 ? (c % Cfg::kChunksPerOff) * 64 : 0;
@@ -261,8 +270,8 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
               if (rw1 >= 0) v[h][rr][1] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)(uint32_t)rw1 * CIN + ehalf + eo1));
             }
         }
-        mbar_wait(bars + kBarEmpty + 8 * s, ph ^ 1u);
-        if (tr) dbg_stamp(p.dbg, gst, 3);
+        mbar_wait_sleep(bars + kBarEmpty + 8 * s, ph ^ 1u);
+        if (TRACE && tr) dbg_stamp(p.dbg, gst, 3);
         if (have) {
           tc_fence_after();
           const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + colA + (uint32_t)((s * 4 + grp) * 32);
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
           tc_fence_before();
         }
         if (lane == 0) mbar_arrive(bars + kBarFull + 8 * s);
-        if (tr) dbg_stamp(p.dbg, gst, 4);
+        if (TRACE && tr) dbg_stamp(p.dbg, gst, 4);
         if (++s == NS) { s = 0; ph ^= 1u; }
       }
       // all index reads of this super-tile are consumed: hand its buffers back
@@ -295,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
         rv[0] = __ldg(rp);
         rv[1] = __ldg(rp + 1);
       }
-      mbar_wait(bars + kBarTFull + 8 * a, (uint32_t)(n / ND) & 1u);
+      mbar_wait_sleep(bars + kBarTFull + 8 * a, (uint32_t)(n / ND) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * COUT;
 #pragma unroll
@@ -358,19 +367,20 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + kBarTEmpty + 8 * a);
-      if (warp == kEpiWarp0 && lane == 0) dbg_stamp(p.dbg, n, 5);
+      if (TRACE && warp == kEpiWarp0 && lane == 0) dbg_stamp(p.dbg, n, 5);
     }
-  } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer =====================
-    // One barrier round per STAGE of 4 chunks (r1 trace: with one round per chunk this warp's own loop — waits,
-    // fence, operand set-up, 4 UTCHMMA, commits: ~110 SASS instructions — took ~600 cycles per chunk and bounded
-    // every layer while the gather ran 8 chunks ahead).
+  } else if (warp == kMmaWarp || warp == kMmaWarp2) {
+    // ===================== MMA issuers =====================
+    // TWO issuing threads, one per row tile of the pass (separate accumulators, so no ordering between them is needed).
+    // Micro-benchmark (scripts/micro/mma_issue_bench.cu): back-to-back tcgen05.mma (M=128, K=16) cost 45 cycles each
+    // for N <= 64 and 64 at N = 128, from tensor or shared memory alike; r1 traces of a single issuing thread showed
+    // 74-90 cycles per MMA because its barrier checks and operand set-up (~100 cycles per check even on a completed
+    // phase) starve the shallow MMA queue.  With two threads one issues while the other looks at barriers.
+    // One barrier round per STAGE of 4 chunks = (c, tile 0), (c, tile 1), (c+1, tile 0), (c+1, tile 1); each thread
+    // issues the two chunks of its tile, both commit to the stage's empty barriers (count 2).
     // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B, N>>3 [17,23), M>>4 [24,29)
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-    // The whole loop runs in ONE elected thread (no per-stage WARPSYNC / ELECT / reconvergence).  A barrier check costs
-    // ~100 cycles even when the phase has long completed and the tcgen05.mma queue is shallow, so the readiness of the
-    // NEXT stage is probed (mbarrier.test_wait, non-blocking) in the middle of issuing the current one: in steady state
-    // the tensor pipe never drains while this thread looks at barriers.
+    const int my_t = warp == kMmaWarp ? 0 : 1;
     if (elect_one_sync()) {
       int s = 0, bs = 0, it = 0, st = 0;
       uint32_t ph = 0, bph = 0;
@@ -378,18 +388,14 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       if (bres) mbar_wait(bars + kBarB, 0);
       const int total = my_super * nst;
       for (int gst = 0; gst < total; ++gst) {
-        const int n0 = it << lT;
-        dbg_stamp(p.dbg, gst, 6);
+        const int n = (it << lT) + my_t;              // tile sequence number of my tile in this pass
+        if (TRACE && my_t == 0) dbg_stamp(p.dbg, gst, 6);
         if (!ready) {
-          if (st == 0)
-            for (int t = 0; t < T; ++t) {
-              const int n = n0 + t;
-              mbar_wait(bars + kBarTEmpty + 8 * (n & (ND - 1)), ((uint32_t)(n / ND) & 1u) ^ 1u);
-            }
+          if (st == 0) mbar_wait(bars + kBarTEmpty + 8 * (n & (ND - 1)), ((uint32_t)(n / ND) & 1u) ^ 1u);
           if (!bres) mbar_wait(bars + kBarBFull + 8 * bs, bph);
           mbar_wait(bars + kBarFull + 8 * s, ph);
         }
-        dbg_stamp(p.dbg, gst, 0);
+        if (TRACE && my_t == 0) dbg_stamp(p.dbg, gst, 0);
         tc_fence_after();
         // ring positions of the next stage
         const int s2 = s + 1 == NS ? 0 : s + 1;
@@ -397,39 +403,31 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
         const int bs2 = bs + 1 == NB ? 0 : bs + 1;
         const uint32_t bph2 = bs + 1 == NB ? bph ^ 1u : bph;
         const bool last_st = st == nst - 1;
-        const int x0 = st * 4;
-        const bool t1_absent = (int)blockIdx.x + it * (int)gridDim.x >= nfull;   // single-tile pass of the split last wave
-        // issue order: the 4 K-slices of one chunk back to back (r1 measurement: interleaving chunks / accumulators
-        // between consecutive MMAs made every MMA ~45 % slower, 109 vs 75 cycles, at every N)
+        const bool absent = my_t == 1 && (int)blockIdx.x + it * (int)gridDim.x >= nfull;   // single-tile pass
+        const uint32_t tmem_d = tmem_base + (uint32_t)((n & (ND - 1)) * COUT);
 #pragma unroll
-        for (int sub = 0; sub < 4; ++sub) {
-          const int x = x0 + sub;
-          if (x < CT) {
-            const int c = x >> lT, t = x & (T - 1);
-            const uint32_t tmem_d = tmem_base + (uint32_t)(((n0 + t) & (ND - 1)) * COUT);
-            const uint32_t tmem_a = tmem_base + colA + (uint32_t)((s * 4 + sub) * 32);
-            const uint64_t bdesc = make_desc_sw128(w_base + (uint32_t)(bres ? c : bs * 2 + (c & 1)) * Cfg::kBBytes);
-            if (!(t == 1 && t1_absent)) {     // the absent second tile of a half pass has nothing to multiply
+        for (int h = 0; h < 2; ++h) {
+          const int c = 2 * st + h;                   // my chunk slot of the stage: sub = 2*h + my_t
+          if (c < nchunks && !absent) {
+            const uint32_t tmem_a = tmem_base + colA + (uint32_t)((s * 4 + 2 * h + my_t) * 32);
+            const uint64_t bdesc = make_desc_sw128(w_base + (uint32_t)(bres ? c : bs * 2 + h) * Cfg::kBBytes);
 #pragma unroll
-              for (int kk = 0; kk < kChunkK / 16; ++kk)
-                umma_bf16_ts(tmem_d, tmem_a + 8 * kk, bdesc + 2 * kk, idesc, (c | kk) != 0 ? 1u : 0u);
-            }
+            for (int kk = 0; kk < kChunkK / 16; ++kk)
+              umma_bf16_ts(tmem_d, tmem_a + 8 * kk, bdesc + 2 * kk, idesc, (c | kk) != 0 ? 1u : 0u);
           }
-          if (sub == 1) {   // probe the next stage while the second half of this one is still to be issued
+          if (h == 0) {   // probe the next stage while the second chunk of this one is still to be issued
             ready = gst + 1 < total && mbar_test(bars + kBarFull + 8 * s2, ph2);
             if (!bres) ready = ready && mbar_test(bars + kBarBFull + 8 * bs2, bph2);
-            if (last_st)
-              for (int t = 0; t < T; ++t) {
-                const int n = n0 + T + t;
-                ready = ready && mbar_test(bars + kBarTEmpty + 8 * (n & (ND - 1)), ((uint32_t)(n / ND) & 1u) ^ 1u);
-              }
+            if (last_st) {
+              const int n2 = n + T;
+              ready = ready && mbar_test(bars + kBarTEmpty + 8 * (n2 & (ND - 1)), ((uint32_t)(n2 / ND) & 1u) ^ 1u);
+            }
           }
         }
         umma_commit(bars + kBarEmpty + 8 * s);
         if (!bres) umma_commit(bars + kBarBEmpty + 8 * bs);
-        if (last_st)
-          for (int t = 0; t < T; ++t) umma_commit(bars + kBarTFull + 8 * ((n0 + t) & (ND - 1)));
-        dbg_stamp(p.dbg, gst, 1);
+        if (last_st) umma_commit(bars + kBarTFull + 8 * (n & (ND - 1)));
+        if (TRACE && my_t == 0) dbg_stamp(p.dbg, gst, 1);
         s = s2;
         ph = ph2;
         if (!bres) { bs = bs2; bph = bph2; }
@@ -444,8 +442,8 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
     const int ntile_seq = my_super << lT;
     for (int n = 0; n < ntile_seq; ++n) {
       const int buf = n & (NI - 1);
-      const int use = n >> (lT + 1);       // how many times this buffer has been filled before
-      if (use > 0) mbar_wait(bars + kBarIdxFree + 8 * buf, (uint32_t)(use - 1) & 1u);
+      const int use = n >> lNI;            // how many times this buffer has been filled before
+      if (use > 0) mbar_wait_sleep(bars + kBarIdxFree + 8 * buf, (uint32_t)(use - 1) & 1u);
       const int tile = tile_of(n);
       const int row0 = tile * kBM + lane * 4;   // this lane: 4 consecutive rows
       const uint32_t dst = idx_base + (uint32_t)buf * idx_buf_bytes + lane * 16;
@@ -488,10 +486,10 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
     }
   }
 
-  if (warp == kMmaWarp && lane == 0) dbg_cta_time(p.dbg, 2);
+  if (TRACE && warp == kMmaWarp && lane == 0) dbg_cta_time(p.dbg, 2);
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) dbg_cta_time(p.dbg, 3);
+  if (TRACE && tid == 0) dbg_cta_time(p.dbg, 3);
   if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -532,17 +530,18 @@ int launch_ts(const ConvFwdArgs& p, cudaStream_t stream) {
   const size_t smem = Cfg::smem_bytes(p.K);
   static thread_local bool configured = false;
   if (!configured) {
-    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
     configured = true;
   }
   if (smem > 227 * 1024 - 1024 || (!Cfg::b_resident(p.K) && Cfg::b_stages(p.K) < 2)) {
     set_error("comb_spconv_fwd_bf16: shared memory %zu exceeds the per-CTA limit", smem);
     return COMB_EINVAL;
   }
-  const int T = Cfg::tiles_per_pass(p.K);
-  const int nsuper = cdiv(cdiv(p.no_max, kBM), T);
+  const int nsuper = cdiv(cdiv(p.no_max, kBM), Cfg::tiles_per_pass(p.K));
   const int grid = nsuper < sm_count() ? nsuper : sm_count();
-  spconv_ts_kernel<CIN, COUT><<<grid, kThreads, smem, stream>>>(p);
+  if (p.dbg != nullptr) spconv_ts_kernel<CIN, COUT, true><<<grid, kThreads, smem, stream>>>(p);   // pipeline trace build
+  else spconv_ts_kernel<CIN, COUT, false><<<grid, kThreads, smem, stream>>>(p);
   COMB_LAUNCH_CHECK();
   return COMB_OK;
 }

@@ -69,5 +69,5 @@ def run(cin, cout, level):
 
 
 if __name__ == "__main__":
-    for cin, cout, lv in ((64, 64, 3), (128, 128, 4)):   # the narrow levels run the warp-MMA kernel (no trace)
+    for cin, cout, lv in ((16, 16, 1), (32, 32, 2), (64, 64, 3), (128, 128, 4)):
         run(cin, cout, lv)
