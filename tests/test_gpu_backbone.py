@@ -208,3 +208,79 @@ def test_frame_stream_matches_synchronous_path():
     for b, f, i, n in got:
         assert n == want[b][0].shape[0]
         assert torch.equal(f, want[b][0]) and torch.equal(i, want[b][1])
+
+
+def _directional_check(net, feats0, coords, scales):
+    """loss = random projection of the encoded tensor and x_conv3; returns [(name, analytic, [difference quotients])]
+    for the voxel features, the first conv weight and a mid-network weight along random unit directions."""
+    proj = {}
+
+    def loss_of(feats):
+        bd = net({"batch_size": 2, "voxel_features": feats, "voxel_coords": coords})
+        out = bd["encoded_spconv_tensor"].features
+        x3 = bd["multi_scale_3d_features"]["x_conv3"].features
+        if not proj:
+            g = torch.Generator(device="cuda").manual_seed(5)
+            proj["o"] = torch.randn(out.shape, device="cuda", generator=g)
+            proj["x3"] = torch.randn(x3.shape, device="cuda", generator=g)
+        return (out * proj["o"]).sum() + 0.1 * (x3 * proj["x3"]).sum()
+
+    feats = feats0.clone().requires_grad_(True)
+    loss_of(feats).backward()
+    w_in, w_mid = net.conv_input[0].weight, net.conv3[1].conv2.weight
+    grads = {"feats": feats.grad.clone(), "w_in": w_in.grad.clone(), "w_mid": w_mid.grad.clone()}
+    assert all(torch.isfinite(g).all() and float(g.abs().sum()) > 0 for g in grads.values())
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    report = []
+    for name, tensor in (("feats", None), ("w_in", w_in), ("w_mid", w_mid)):
+        base = feats0 if tensor is None else tensor.detach()
+        d = torch.randn(base.shape, device="cuda", generator=gen)
+        d = d / d.norm()
+        an = float((grads[name] * d).sum())
+        fds = []
+        for scale in scales:
+            eps = scale * float(base.norm())
+            with torch.no_grad():
+                if tensor is None:
+                    lp, lm = float(loss_of(feats0 + eps * d)), float(loss_of(feats0 - eps * d))
+                else:
+                    tensor.add_(eps * d)
+                    lp = float(loss_of(feats0))
+                    tensor.sub_(2 * eps * d)
+                    lm = float(loss_of(feats0))
+                    tensor.add_(eps * d)
+            fds.append((lp - lm) / (2 * eps))
+        report.append((name, an, fds))
+    return report
+
+
+def test_backbone_forward_backward_train_mode(setup):
+    """a8 at backbone scale (BASELINE configs[2], the sparse part of a training step): VoxelResBackBone8x in TRAIN mode
+    (module path: fp32 sparse convs with autograd, BatchNorm1d batch statistics) runs forward + backward through all 21
+    sparse convolutions.  (a) With the ReLUs replaced by the identity the loss is smooth, and the gradients w.r.t. the
+    voxel features and two conv weights must match central finite differences of the same fp32 forward to 1e-2 — this
+    pins the composition of dgrad / wgrad / rulebook transposes / autograd plumbing (the per-layer arithmetic is held
+    to 1e-4 in test_gpu_spconv.py).  (b) With the real ReLUs the loss is piecewise linear with millions of kinks, so
+    the difference quotient only approaches the derivative (measured -0.185 / -0.260 / -0.314 at steps 3e-3 / 7.5e-4 /
+    1.9e-4 against an analytic -0.303): the small-step quotient is held to 15 %."""
+    frames, pipe, sd, ref_levels, ref_sf, ref_coords = setup
+    offs = [0, len(frames[0]), len(frames[0]) + len(frames[1])]
+    r = ops.voxelize(torch.from_numpy(np.concatenate(frames)).cuda(), offs, VSIZE, RANGE, 5, 40000)
+    m = int(r["counts"][2])
+    feats0 = models.MeanVFE(None, 5)({"voxels": r["voxels"][:m], "voxel_num_points": r["num_points"][:m]})["voxel_features"]
+    coords = r["coords"][:m].float()
+    for smooth in (True, False):
+        torch.manual_seed(11)
+        net = models.VoxelResBackBone8x(None, 5, pipe.grid_size).cuda().train()
+        net.fused = False
+        if smooth:
+            for mod in list(net.modules()):
+                for cname, child in list(mod.named_children()):
+                    if isinstance(child, torch.nn.ReLU):
+                        setattr(mod, cname, torch.nn.Identity())
+        report = _directional_check(net, feats0, coords, (3e-3,) if smooth else (1.875e-4,))
+        print("fd report smooth=%s" % smooth, report)
+        tol = 1e-2 if smooth else 0.15
+        for name, an, fds in report:
+            assert abs(fds[0] - an) <= tol * max(abs(fds[0]), abs(an)) + 1e-3, (smooth, report)

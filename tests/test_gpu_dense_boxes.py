@@ -140,3 +140,60 @@ def test_nms_wrapper_matches_model_nms_utils_contract():
     assert iou.max() <= 0.7 + 1e-3            # survivors do not suppress each other
     empty, _ = box_ops.nms_gpu(boxes[:0], scores[:0], 0.7)
     assert empty.numel() == 0
+
+
+def test_config4_comaug_collision_checks_full_size():
+    """BASELINE configs[3]: COMAug GT sampling — 10 000 candidate boxes against 100 existing boxes (bit-exact vs the
+    oracle, which finishes this in < 1 s) and against each other (10k x 10k = 1e8 pairs: 60 random 64x64 blocks
+    bit-exact vs the oracle, plus size-independent properties of the whole matrix), then points_in_boxes removal of
+    the surviving <= 35 boxes on a 180k-point frame."""
+    cand = np.concatenate([synth.make_clustered_boxes(9000, seed=61, centers=400), synth.make_boxes(1000, seed=64)]).astype(np.float32)
+    exist = synth.make_clustered_boxes(100, seed=62, centers=400)
+    got = box_ops.boxes_bev_iou_cpu(cand, exist)
+    want = oracle.boxes_bev_cpu(cand, exist)
+    assert (want > 0).sum() > 500
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    full = box_ops.boxes_bev_iou_cpu(cand, cand)                      # (10000, 10000) float32, 400 MB
+    assert full.shape == (10000, 10000)
+    rng = np.random.default_rng(63)
+    for _ in range(60):
+        i0, j0 = rng.integers(0, 10000 - 64, size=2)
+        if rng.uniform() < 0.5:
+            j0 = i0                                                   # diagonal blocks hold the dense overlaps
+        blk = oracle.boxes_bev_cpu(cand[i0:i0 + 64], cand[j0:j0 + 64])
+        assert np.array_equal(full[i0:i0 + 64, j0:j0 + 64].view(np.uint32), blk.view(np.uint32))
+    d = np.diagonal(full)
+    assert np.all(np.abs(d - 1.0) < 1e-4)                             # IoU(box, box) = 1 (SURVEY §8c known answer)
+    assert np.all(full >= 0) and np.all(full <= 1.0 + 1e-4)
+    # boxes whose centres are further apart than the sum of their half diagonals cannot overlap: exactly 0
+    c = cand[:2000]
+    rad = 0.5 * np.hypot(c[:, 3], c[:, 4])
+    dist = np.hypot(c[:, None, 0] - c[None, :, 0], c[:, None, 1] - c[None, :, 1])
+    far = dist > (rad[:, None] + rad[None, :]) + 0.05
+    assert np.all(full[:2000, :2000][far] == 0)
+    # collision-free survivors (what database_sampler_v2.py:600-604 keeps), then remove their points from the frame
+    ok = (got.max(axis=1) == 0)
+    iou_self = full.copy()
+    np.fill_diagonal(iou_self, 0)
+    survivors = cand[ok & (iou_self.max(axis=1) == 0)][:35]
+    assert len(survivors) > 0
+    pts = synth.make_frame(seed=1003)
+    survivors[:, 2] = -1.0
+    kept = box_ops.remove_points_in_boxes3d(pts, survivors)
+    inside = oracle.points_in_boxes_cpu(pts[:, :3].copy(), survivors)
+    assert np.array_equal(kept, pts[inside.sum(0) == 0])
+
+
+def test_nms_api_maximum_size():
+    """nms_gpu at the API maximum of class_agnostic_nms (NMS_PRE_MAXSIZE 4096, centerpoint.yaml:61-69): CPU flavour
+    vs the oracle's greedy sweep at 4096 boxes, and idempotence (NMS of the kept set keeps everything)."""
+    boxes = synth.make_clustered_boxes(4096, seed=71, centers=40)
+    trig = cuda(ops.box_trig4_host(boxes))
+    for thresh in (0.1, 0.7):
+        want = oracle.nms_cpu(boxes, thresh)
+        keep, num = ops.nms(cuda(boxes), thresh, rotated=True, flavour="cpu", trig=trig)
+        got = keep[: int(num)].cpu().numpy()
+        assert np.array_equal(got, want) and 100 < len(want) < 4000
+        kb = boxes[got]
+        keep2, num2 = ops.nms(cuda(kb), thresh, rotated=True, flavour="cpu", trig=cuda(ops.box_trig4_host(kb)))
+        assert int(num2) == len(kb) and np.array_equal(keep2[: int(num2)].cpu().numpy(), np.arange(len(kb)))

@@ -139,3 +139,19 @@ def test_device_side_frame_offsets():
     n = int(a["counts"][-1])
     for k in ("voxels", "coords", "num_points", "mean"):
         assert torch.equal(a[k][:n], b[k][:n])
+
+
+_sweep3 = {}
+
+
+@pytest.mark.parametrize("cap", [100000, 180000, 400000])
+def test_config5_three_sweep_frame_full_size(cap):
+    """BASELINE configs[4]: 3-sweep aggregated frame (~500k points x 6 features incl. the timestamp channel) with the
+    multiframe voxel caps of waymo_dataset_multiframe.yaml:83-89 (and a smaller one that truncates) — bit-exact vs the oracle (coordinates, first-5
+    point assignment, counts, first-`cap` voxels in order of first appearance)."""
+    if "pts" not in _sweep3:
+        _sweep3["pts"] = synth.make_frame(seed=1005, sweeps=3)
+    pts = _sweep3["pts"]
+    assert pts.shape[1] == 6 and 420000 < len(pts) < 600000
+    m = check_frames([pts], WAYMO_VSIZE, WAYMO_RANGE, 5, cap)
+    assert m == min(cap, 144913)          # 144 913 voxels on this frame: the 100 000 cap truncates, the others do not
