@@ -16,6 +16,8 @@ VoxelResBackBone8x has two execution modes:
 """
 from functools import partial
 
+import os
+
 import torch
 from torch import nn
 
@@ -122,6 +124,7 @@ class VoxelResBackBone8x(nn.Module):
         self.backbone_channels = {'x_conv1': 16, 'x_conv2': 32, 'x_conv3': 64, 'x_conv4': 128}
         self._plan = None
         self._ratios = {}
+        self._side = None       # side stream of the coordinate chain (see _run_fused)
 
     # ------------------------------------------------------------------ reference-shaped forward
     def forward(self, batch_dict):
@@ -183,46 +186,88 @@ class VoxelResBackBone8x(nn.Module):
     def _run_fused(self, feats, coords, batch_size, caps, n_dev=None):
         """Every level keeps its rows in KEY ORDER (ascending ((b*D+z)*H+y)*W+x): level 1 is permuted from
         voxel order once, strided levels are emitted in key order by the bitmap index.  Spatially ordered rows
-        make the gathers of a 128-row tile hit neighbouring memory, and the bitmap-rank index replaces hashing."""
+        make the gathers of a 128-row tile hit neighbouring memory, and the bitmap-rank index replaces hashing.
+
+        Two streams: everything that depends on COORDINATES only (the bitmap indices, output sets and rulebooks of
+        all levels, ~25 % of the step) is enqueued on a side stream and runs ahead; the launch stream carries the
+        feature chain (permute + 21 convs) and waits, per level, on the event of the rulebook it needs.  The small
+        index / rulebook kernels then fill the tails of the persistent conv kernels instead of sitting between them.
+        Inside a CUDA-graph capture this becomes a fork/join of the graph (COMB_OVERLAP=0 keeps one stream)."""
         plan = self._get_plan()
         if feats.dtype == torch.bfloat16 and feats.shape[1] == 16:
             x = feats.contiguous()
         else:
             x = ops.cast_pad(feats.float().contiguous(), 16)
         k3, one = [3, 3, 3], [1, 1, 1]
-        shape = list(self.sparse_shape)
-        idx = ops.index_build(coords.contiguous(), batch_size, shape, n_dev=n_dev)
-        perm = ops.index_rank(coords, idx, n_dev=n_dev)
+        main = torch.cuda.current_stream(feats.device)
+        overlap = os.environ.get("COMB_OVERLAP", "1") != "0"
+        if overlap:
+            if self._side is None or self._side.device != feats.device:
+                self._side = torch.cuda.Stream(feats.device)
+            side = self._side
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+        else:
+            side = main
+
+        def handoff(*tensors):
+            """event after which the launch stream may use tensors produced on the side stream"""
+            if not overlap:
+                return None
+            for t in tensors:
+                if t is not None:
+                    t.record_stream(main)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            return ev
+
+        def wait(ev):
+            if ev is not None:
+                main.wait_event(ev)
+
+        # ---- coordinate chain (side stream) ----------------------------------------------------------------------
+        steps = []          # per level: dict(coords, count, shape, nbr, ev_nbr, nbr_d, ev_d)
+        with torch.cuda.stream(side):
+            shape = list(self.sparse_shape)
+            idx = ops.index_build(coords.contiguous(), batch_size, shape, n_dev=n_dev)
+            perm = ops.index_rank(coords, idx, n_dev=n_dev)
+            ev_perm = handoff(perm, idx.coords, idx.count)
+            cur_coords, cur_n = idx.coords, idx.count
+            convs = {2: plan['down2'], 3: plan['down3'], 4: plan['down4'], 5: plan['out']}
+            for li in (1, 2, 3, 4, 5):
+                st = {}
+                if li > 1:
+                    conv = convs[li]['conv']
+                    cv = (conv.kernel_size, conv.stride, conv.padding, conv.dilation)
+                    oshape = ops.conv_out_shape(shape, *cv)
+                    oidx = ops.index_build(cur_coords, batch_size, oshape, conv=cv, out_cap=caps[li], n_dev=cur_n)
+                    st['nbr_d'] = ops.nbrmap_build_indexed(oidx.coords, idx, *cv, no_dev=oidx.count)
+                    st['ev_d'] = handoff(st['nbr_d'], oidx.coords, oidx.count)
+                    idx, cur_coords, cur_n, shape = oidx, oidx.coords, oidx.count, oshape
+                if li < 5:
+                    st['nbr'] = ops.nbrmap_build_indexed(cur_coords, idx, k3, one, one, one, no_dev=cur_n)
+                    st['ev_nbr'] = handoff(st['nbr'])
+                st.update(coords=cur_coords, count=cur_n, shape=list(shape))
+                steps.append(st)
+
+        # ---- feature chain (launch stream) -----------------------------------------------------------------------
+        wait(ev_perm)
         x = ops.permute_rows(x, perm, scatter=True, n_dev=n_dev)
-        cur_coords, cur_n = idx.coords, idx.count
-        levels, counts = [], [idx.count]
-        for li in (1, 2, 3, 4):
+        levels, counts = [], []
+        for li, st in zip((1, 2, 3, 4, 5), steps):
             if li > 1:
-                spec = plan['down%d' % li]
-                conv = spec['conv']
-                cv = (conv.kernel_size, conv.stride, conv.padding, conv.dilation)
-                oshape = ops.conv_out_shape(shape, *cv)
-                oidx = ops.index_build(cur_coords, batch_size, oshape, conv=cv, out_cap=caps[li], n_dev=cur_n)
-                nbr_d = ops.nbrmap_build_indexed(oidx.coords, idx, *cv, no_dev=oidx.count)
-                x = self._conv(x, spec, nbr_d, oidx.count)
-                idx, cur_coords, cur_n, shape = oidx, oidx.coords, oidx.count, oshape
-                counts.append(oidx.count)
-            nbr = ops.nbrmap_build_indexed(cur_coords, idx, k3, one, one, one, no_dev=cur_n)
-            if li == 1:
-                x = self._conv(x, plan['input'], nbr, cur_n)
-            for (c1, c2) in plan['res%d' % li]:
-                y = self._conv(x, c1, nbr, cur_n)
-                x = self._conv(y, c2, nbr, cur_n, residual=x)
-            levels.append((x, cur_coords, list(shape)))
-        spec = plan['out']
-        conv = spec['conv']
-        cv = (conv.kernel_size, conv.stride, conv.padding, conv.dilation)
-        oshape = ops.conv_out_shape(shape, *cv)
-        oidx = ops.index_build(cur_coords, batch_size, oshape, conv=cv, out_cap=caps[5], n_dev=cur_n)
-        nbr_d = ops.nbrmap_build_indexed(oidx.coords, idx, *cv, no_dev=oidx.count)
-        x = self._conv(x, spec, nbr_d, oidx.count)
-        counts.append(oidx.count)
-        levels.append((x, oidx.coords, list(oshape)))
+                wait(st['ev_d'])
+                x = self._conv(x, convs[li], st['nbr_d'], st['count'])
+            counts.append(st['count'])
+            if li < 5:
+                wait(st['ev_nbr'])
+                if li == 1:
+                    x = self._conv(x, plan['input'], st['nbr'], st['count'])
+                for (c1, c2) in plan['res%d' % li]:
+                    y = self._conv(x, c1, st['nbr'], st['count'])
+                    x = self._conv(y, c2, st['nbr'], st['count'], residual=x)
+            levels.append((x, st['coords'], st['shape']))
         return levels, torch.cat(counts)
 
     def _caps(self, n1, batch_size, worst):

@@ -99,6 +99,30 @@ class FramePipeline:
             out = self._finish(self._enqueue(points, frame_offsets, batch, worst=True), batch)
         return out
 
+    @torch.no_grad()
+    def enqueue_device(self, points, frame_offsets):
+        """Asynchronous form of forward_device in CUDA-graph mode: copy the (device or pinned host) points into the
+        graph's input buffer and replay, WITHOUT reading the row counts back — returns a handle for finish().  Steps
+        enqueued back to back run on the device with no host round trip in between."""
+        if not self.use_graph:
+            raise RuntimeError("enqueue_device needs FramePipeline(use_graph=True)")
+        batch, n = len(frame_offsets) - 1, int(points.shape[0])
+        g = self._graph
+        if g is None or g["batch"] != batch or n > g["n_cap"]:
+            g = self._capture(points.to(self.device, non_blocking=True), frame_offsets, batch)
+        g["points"][:n].copy_(points, non_blocking=True)
+        g["offs_host"][: batch + 1] = torch.tensor(frame_offsets, dtype=torch.int32)
+        g["offs"].copy_(g["offs_host"], non_blocking=True)
+        g["graph"].replay()
+        self.graph_launches += g["launches"]
+        return (g, batch)
+
+    def finish(self, handle):
+        """Read the row counts of the LAST replay of the handle's graph and build the batch_dict (None when a learned
+        capacity overflowed: call forward_device for that batch)."""
+        g, batch = handle
+        return self._finish(g["q"], batch)
+
     def _capture(self, points, frame_offsets, batch):
         n = int(points.shape[0])
         n_cap = max((int(n * 1.25) + 65535) // 65536 * 65536, 65536)
