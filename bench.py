@@ -143,7 +143,9 @@ class EventProfiler:
             return dict(n=info["n"], C=info["C"], T=info["T"], M=c[-1], mean_ld=info["mean_ld"],
                         mean_bytes=info["mean_bytes"], want_voxels=bool(info["want_voxels"]))
         if tag == "dense":
-            return dict(n=info["n"], C=info["C"], cells=info["cells"], in_bytes=info["in_bytes"])
+            n = int(info["n_dev"].item()) if info.get("n_dev") is not None else info["n"]
+            return dict(n=min(n, info["n"]), C=info["C"], cells=info["cells"], in_bytes=info["in_bytes"],
+                        scatter=bool(info.get("scatter", False)))
         if tag == "nbrmap_build":
             n = int(info["no_dev"].item()) if info["no_dev"] is not None else info["no"]
             return dict(no=min(n, info["no"]), K=info["K"])
@@ -178,6 +180,8 @@ def algorithmic(tag, m):
             by += m["M"] * m["T"] * m["C"] * 4.0
         return by, 0.0
     if tag == "dense":
+        if m.get("scatter"):      # scatter into the pre-zeroed tensor (the zero-fill is a memset off the critical path)
+            return m["n"] * m["C"] * (m["in_bytes"] + 4.0) + m["n"] * 16.0, 0.0
         return m["cells"] * m["C"] * 4.0 + m["n"] * m["C"] * m["in_bytes"] + m["n"] * 16.0, 0.0
     if tag == "nbrmap_build":
         return m["no"] * 16.0 + m["no"] * m["K"] * 4.0, 0.0

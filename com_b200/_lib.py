@@ -56,6 +56,7 @@ SIGNATURES = {
     "comb_affine_relu": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, _P, c_int, _P, _P]),
     "comb_cast_pad": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P]),
     "comb_dense": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "comb_dense_scatter": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "comb_dense_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "comb_box_trig_host": (None, [_PF, c_int, _PF]),
     "comb_points_in_boxes_mask": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, _P]),

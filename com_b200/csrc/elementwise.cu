@@ -204,6 +204,50 @@ extern "C" int comb_permute_rows(const void* in, const int* row_map, int n_max, 
   return COMB_OK;
 }
 
+// Scatter form of dense(): `out` is already zero (the caller clears it early, off the critical path, e.g. with
+// cudaMemsetAsync on a side stream) and only the active cells are written.  One thread per (row, 8-channel group):
+// one 16-byte load of the row's channels, 8 stores into 8 channel planes; lanes of a warp are CONSECUTIVE rows, and
+// with rows in key order consecutive rows are x-neighbours, so a warp's stores into one plane land in one or two
+// sectors.  Algorithmic bytes: n*C*(in + 4) + n*16 instead of the full B*C*D*H*W*4 rewrite.
+template <typename T>
+__global__ void __launch_bounds__(256) dense_scatter_kernel(const T* __restrict__ feats, const int4* __restrict__ coords,
+                                                             int n_max, const int* __restrict__ n_dev, int batch, int C,
+                                                             int D, int H, int W, float* __restrict__ out) {
+  const int n = eff_n(n_max, n_dev);
+  const int groups = (C + 7) >> 3;
+  const long long total = (long long)groups * ((n + 31) & ~31);
+  const long long DHW = (long long)D * H * W;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    // 32 consecutive rows x one channel group per warp
+    const int row = (int)((e >> 5) / groups) * 32 + (int)(e & 31);
+    const int g = (int)((e >> 5) % groups);
+    if (row >= n) continue;
+    const int4 c = __ldg(coords + row);
+    if ((unsigned)c.x >= (unsigned)batch || (unsigned)c.y >= (unsigned)D || (unsigned)c.z >= (unsigned)H ||
+        (unsigned)c.w >= (unsigned)W)
+      continue;
+    float v[8];
+    const int c0 = g * 8;
+    if (sizeof(T) == 2 && (C & 7) == 0) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(feats + (size_t)row * C + c0));
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h2[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = c0 + i < C ? (float)feats[(size_t)row * C + c0 + i] : 0.0f;
+    }
+    float* o = out + ((size_t)c.x * C + c0) * DHW + ((size_t)c.y * H + c.z) * W + c.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (c0 + i < C) o[(size_t)i * DHW] = v[i];
+  }
+}
+
 extern "C" size_t comb_dense_workspace_bytes(int batch, int D, int H, int W) {
   if (batch < 1 || D < 1 || H < 1 || W < 1) return 0;
   return align_up((size_t)batch * D * H * W * 4, 256);
@@ -251,6 +295,28 @@ extern "C" int comb_dense(const void* feats, int dtype, const int* coords, int n
                                                                               C, DHW, tiles_per_frame, out);
   else
     COMB_CHECK_ARG(false, "comb_dense: unknown dtype %d", dtype);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}
+
+extern "C" int comb_dense_scatter(const void* feats, int dtype, const int* coords, int n_max, const int* n_dev,
+                                  int batch, int C, int D, int H, int W, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(batch >= 1 && C >= 1 && D >= 1 && H >= 1 && W >= 1 && n_max >= 0, "comb_dense_scatter: bad shape");
+  COMB_CHECK_ARG(out, "comb_dense_scatter: null pointer");
+  if (n_max == 0) return COMB_OK;
+  COMB_CHECK_ARG(feats && coords, "comb_dense_scatter: null feats/coords");
+  const long long total = (long long)((C + 7) / 8) * ((n_max + 31) / 32 * 32);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (dtype == COMB_DT_F32)
+    dense_scatter_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>((const float*)feats, (const int4*)coords, n_max, n_dev,
+                                                                       batch, C, D, H, W, out);
+  else if (dtype == COMB_DT_BF16)
+    dense_scatter_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)feats, (const int4*)coords,
+                                                                                n_max, n_dev, batch, C, D, H, W, out);
+  else
+    COMB_CHECK_ARG(false, "comb_dense_scatter: unknown dtype %d", dtype);
   COMB_LAUNCH_CHECK();
   return COMB_OK;
 }

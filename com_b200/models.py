@@ -270,6 +270,13 @@ class VoxelResBackBone8x(nn.Module):
             levels.append((x, st['coords'], st['shape']))
         return levels, torch.cat(counts)
 
+    def out_spatial_shape(self):
+        """[D, H, W] of the encoded tensor: sparse_shape through the four strided convolutions."""
+        shape = list(self.sparse_shape)
+        for conv in (self.conv2[0][0], self.conv3[0][0], self.conv4[0][0], self.conv_out[0]):
+            shape = ops.conv_out_shape(shape, conv.kernel_size, conv.stride, conv.padding, conv.dilation)
+        return [int(v) for v in shape]
+
     def _caps(self, n1, batch_size, worst):
         """Row capacities of levels 2..4 and the output level for this call."""
         shape = list(self.sparse_shape)

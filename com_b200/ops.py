@@ -430,6 +430,22 @@ def dense(feats, coords, batch, shape, n_dev=None):
     return out
 
 
+def dense_scatter(feats, coords, batch, shape, out, n_dev=None):
+    """Scatter the rows into `out` (batch, C, D, H, W) fp32, which the caller has ALREADY zeroed (see
+    FramePipeline._enqueue: the zero-fill runs early on the side stream)."""
+    lib = _lib.load()
+    _need(feats, feats.dtype, "feats")
+    _need(coords, torch.int32, "coords")
+    _need(out, torch.float32, "out")
+    D, H, W = [int(x) for x in shape]
+    n, C = int(feats.shape[0]), int(feats.shape[1])
+    assert tuple(out.shape) == (int(batch), C, D, H, W)
+    with _Scope("dense", n=n, n_dev=n_dev, C=C, cells=int(batch) * D * H * W, in_bytes=feats.element_size(), scatter=True):
+        check(lib.comb_dense_scatter(_p(feats), _dt(feats), _p(coords), n, _p(n_dev), int(batch), C, D, H, W, _p(out),
+                                     _stream()), "comb_dense_scatter")
+    return out
+
+
 # --------------------------------------------------------------------------------------------- box ops
 def box_trig_host(boxes_np):
     """(nb,2) float32 = (cosf(-rz), sinf(-rz)) from the host libm (bit-identical to the reference's)."""

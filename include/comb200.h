@@ -215,6 +215,10 @@ int comb_dense(const void* feats, int dtype, const int* coords, int n_max, const
                int batch, int C, int D, int H, int W, float* out, void* workspace,
                size_t workspace_bytes, void* stream);
 size_t comb_dense_workspace_bytes(int batch, int D, int H, int W);
+/* Scatter form of the same operation: `out` must already be zero (clear it early, off the critical path — the
+ * zero-fill of the 36 MB/frame BEV tensor does not depend on the features); only the active cells are written. */
+int comb_dense_scatter(const void* feats, int dtype, const int* coords, int n_max, const int* n_dev,
+                       int batch, int C, int D, int H, int W, float* out, void* stream);
 
 /* ---- a11/a12: points in boxes -----------------------------------------------------------------
  * comb_points_in_boxes_mask replaces points_in_boxes_cpu (pcdet/ops/roiaware_pool3d/src/

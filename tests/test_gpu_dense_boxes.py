@@ -197,3 +197,20 @@ def test_nms_api_maximum_size():
         kb = boxes[got]
         keep2, num2 = ops.nms(cuda(kb), thresh, rotated=True, flavour="cpu", trig=cuda(ops.box_trig4_host(kb)))
         assert int(num2) == len(kb) and np.array_equal(keep2[: int(num2)].cpu().numpy(), np.arange(len(kb)))
+
+
+@pytest.mark.parametrize("C,dtype", [(128, torch.bfloat16), (128, torch.float32), (5, torch.float32), (33, torch.float32)])
+def test_dense_scatter_matches_dense(C, dtype):
+    """comb_dense_scatter into a pre-zeroed tensor == comb_dense (bit-exact), incl. a device-side row count."""
+    rng = np.random.default_rng(C)
+    shape = [2, 47, 45]
+    coords = random_coords(rng, 3000, 3, shape)
+    coords = coords[np.lexsort((coords[:, 3], coords[:, 2], coords[:, 1], coords[:, 0]))]
+    feats = cuda(rng.normal(size=(len(coords), C)).astype(np.float32)).to(dtype)
+    want = ops.dense(feats, cuda(coords), 3, shape)
+    out = torch.zeros_like(want)
+    got = ops.dense_scatter(feats, cuda(coords), 3, shape, out)
+    assert torch.equal(got, want)
+    n_dev = torch.tensor([1234], dtype=torch.int32, device="cuda")
+    out2 = ops.dense_scatter(feats, cuda(coords), 3, shape, torch.zeros_like(want), n_dev=n_dev)
+    assert torch.equal(out2, ops.dense(feats[:1234].contiguous(), cuda(coords[:1234]), 3, shape))
