@@ -86,7 +86,28 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
 
+    def _run_nvml(self):
+        """fast path: NVML through nvidia_ml_py (a sample every ~5 ms instead of one nvidia-smi process per 0.2-1 s)"""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        while not self._stop_evt.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            r = int(get_reasons(h))
+            self.rows.append([str(sm), str(mx)] + [("Active" if r & bits[n] else "Not Active") for n in
+                                                   ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+            self._stop_evt.wait(0.005)
+
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         while not self._stop_evt.is_set():
             try:
                 o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -228,6 +249,7 @@ def reference_arm(args):
         return
     import oracle
     oracle.build()
+    oracle.fast().orc_fast_set_threads(int(os.cpu_count() or 1))   # torchrun exports OMP_NUM_THREADS=1: use every host core
     cores = oracle.fast().orc_fast_threads()
     frames = make_frames([1000])
     sd = cpu_state_dict()
@@ -437,6 +459,7 @@ def ours(args):
             import oracle
             oracle.build()
             sd = {k: v.detach().cpu() for k, v in pipe.backbone.state_dict().items()}
+            oracle.fast().orc_fast_set_threads(int(os.cpu_count() or 1))
             cores = oracle.fast().orc_fast_threads()
             cpu_run_frames(frames[:1], sd)
             reps = 2
