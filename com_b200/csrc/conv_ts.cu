@@ -266,6 +266,8 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
               }
               v[h][rr][0] = make_uint4(0u, 0u, 0u, 0u);
               v[h][rr][1] = make_uint4(0u, 0u, 0u, 0u);
+              // (r1 A/B: 8-byte loads that land directly in the register pairs of the tcgen05.st fragment remove the 32
+              // register moves per chunk but double the load instructions: 5 % SLOWER, the LSU is the next limit)
               if (rw0 >= 0) v[h][rr][0] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)(uint32_t)rw0 * CIN + ehalf + eo0));
               if (rw1 >= 0) v[h][rr][1] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)(uint32_t)rw1 * CIN + ehalf + eo1));
             }

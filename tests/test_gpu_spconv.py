@@ -155,3 +155,37 @@ def test_module_autograd_matches_oracle():
     Wi = inv.weight.detach().reshape(16, 27, 32).cpu().numpy()
     want = oracle.conv_fwd(y.features.detach().cpu().numpy(), Wi, ops.nbrmap_transpose(cuda(nbr), len(coords)).cpu().numpy())
     assert rel_err(z.features.detach().cpu().numpy(), want) < TOL_F32
+
+
+@pytest.mark.parametrize("env", [{"COMB_CONV_IMPL": "ss"}, {"COMB_CONV_NARROW": "wm"}])
+def test_alternate_conv_kernels_stay_correct(env):
+    """The documented A/B switches (shared-memory-A tcgen05 kernel, warp-level mma.sync kernel for the narrow levels)
+    are read once per process, so each is exercised in a child process: bf16 forward vs the oracle, 1e-4."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, "tests")
+import oracle
+from com_b200 import ops
+from util import clustered_coords
+rng = np.random.default_rng(5)
+shape = [12, 40, 40]
+coords = clustered_coords(rng, 3000, 2, shape, clusters=10, spread=2.5)
+nbr = oracle.subm_nbrmap(coords, shape)
+bf = lambda a: torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+for cin, cout in ((16, 16), (32, 32), (64, 64)):
+    feats = rng.normal(size=(len(coords), cin)).astype(np.float32)
+    W = (rng.normal(size=(cout, 27, cin)) / np.sqrt(27 * cin)).astype(np.float32)
+    want = oracle.conv_fwd(bf(feats), bf(W), nbr)
+    got = ops.spconv_fwd_bf16(ops.cast_pad(torch.from_numpy(feats).cuda(), cin), ops.pack_weight_bf16(torch.from_numpy(W).cuda()),
+                              27, cout, torch.from_numpy(nbr).cuda(), out_dtype=torch.float32).cpu().numpy()
+    err = float(np.abs(got - want).max() / np.abs(want).max())
+    assert err < 1e-4, (cin, cout, err)
+print("alt-ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, PYTHONPATH=root, **env),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "alt-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
