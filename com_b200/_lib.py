@@ -42,6 +42,7 @@ SIGNATURES = {
     "comb_index_build": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _PI, _PI, _PI, _PI, _P, _P, _P, c_int, _P,
                                  _P]),
     "comb_index_rank": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "comb_index_rank_scatter": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P]),
     "comb_nbrmap_build_indexed": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _PI, _PI, _PI, _PI, _P,
                                           c_int, _P]),
     "comb_permute_rows": (c_int, [_P, _P, c_int, _P, c_int, c_int, _P, _P]),

@@ -245,6 +245,20 @@ __global__ void __launch_bounds__(256) index_emit_kernel(const uint32_t* __restr
   }
 }
 
+// Prefix finalisation alone (no coordinates wanted): one thread per rank block.  Used for the level-1 index, whose
+// rows in key order are produced by comb_index_rank_scatter from the voxel list instead of by enumerating a 46 MB
+// bitmap (r1 ncu: the enumerating emit kernel took 51 us on that bitmap, the rank kernel 9 us).
+__global__ void __launch_bounds__(256) index_finalize_kernel(int nblks, const int* __restrict__ bprefix_local,
+                                                              int* __restrict__ bprefix,
+                                                              const int* __restrict__ super_off) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblks) return;
+  const int sb = b / kSuperBlks;
+  const int off = __ldg(super_off + sb);
+  const bool sb_empty = (__ldg(super_off + sb + 1) == off);
+  bprefix[b] = off + (sb_empty ? 0 : __ldg(bprefix_local + b));
+}
+
 // row of `key` (its bit is known to be set, or use only if you tested it)
 __device__ __forceinline__ int index_rank(const uint32_t* __restrict__ bitmap, const int* __restrict__ bprefix,
                                           uint32_t key) {
@@ -268,7 +282,8 @@ __device__ __forceinline__ int index_rank(const uint32_t* __restrict__ bitmap, c
 __global__ void __launch_bounds__(256) index_rank_kernel(const int4* __restrict__ coords, int n_max,
                                                           const int* __restrict__ n_dev, int batch, int D, int H, int W,
                                                           const uint32_t* __restrict__ bitmap,
-                                                          const int* __restrict__ bprefix, int* __restrict__ rows) {
+                                                          const int* __restrict__ bprefix, int* __restrict__ rows,
+                                                          int4* __restrict__ sorted_coords, int sorted_cap) {
   const int n = eff_n(n_max, n_dev);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -280,6 +295,8 @@ __global__ void __launch_bounds__(256) index_rank_kernel(const int4* __restrict_
     if (__ldg(bitmap + (key >> 5)) & (1u << (key & 31))) r = index_rank(bitmap, bprefix, key);
   }
   rows[i] = r;
+  // unique coordinates land on distinct rows: the coordinate list in key order, without enumerating the bitmap
+  if (sorted_coords != nullptr && r >= 0 && r < sorted_cap) sorted_coords[r] = c;
 }
 
 // nbr[k][o] = row of coordinate o*s - p + k*d in the input level, by bitmap test + rank.  One thread per output
@@ -424,8 +441,11 @@ extern "C" int comb_index_build(const int* coords, int n_max, const int* n_dev, 
   COMB_LAUNCH_CHECK();
   index_scan_kernel<<<1, 1024, 0, stream>>>(super, d.nsuper, out_cap, out_count);
   COMB_LAUNCH_CHECK();
-  index_emit_kernel<<<cdiv(d.nwords, 256), 256, 0, stream>>>(bm, d.nwords, blocal, bprefix, super, D, H, W, out_cap,
-                                                             (int4*)out_coords);
+  if (out_coords == nullptr)
+    index_finalize_kernel<<<cdiv(d.nblks, 256), 256, 0, stream>>>(d.nblks, blocal, bprefix, super);
+  else
+    index_emit_kernel<<<cdiv(d.nwords, 256), 256, 0, stream>>>(bm, d.nwords, blocal, bprefix, super, D, H, W, out_cap,
+                                                               (int4*)out_coords);
   COMB_LAUNCH_CHECK();
   return COMB_OK;
 }
@@ -439,7 +459,23 @@ extern "C" int comb_index_rank(const int* coords, int n_max, const int* n_dev, i
   if (n_max == 0) return COMB_OK;
   COMB_CHECK_ARG(coords && bitmap && prefix && rows, "comb_index_rank: null pointer");
   index_rank_kernel<<<cdiv(n_max, 256), 256, 0, stream>>>((const int4*)coords, n_max, n_dev, batch, D, H, W,
-                                                          (const uint32_t*)bitmap, (const int*)prefix, rows);
+                                                          (const uint32_t*)bitmap, (const int*)prefix, rows, nullptr, 0);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}
+
+extern "C" int comb_index_rank_scatter(const int* coords, int n_max, const int* n_dev, int batch, int D, int H, int W,
+                                       const void* bitmap, const void* prefix, int* rows, int* sorted_coords,
+                                       int sorted_cap, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(n_max >= 0 && sorted_cap >= 0, "comb_index_rank_scatter: bad arguments");
+  int rc = check_volume("comb_index_rank_scatter", batch, D, H, W);
+  if (rc) return rc;
+  if (n_max == 0) return COMB_OK;
+  COMB_CHECK_ARG(coords && bitmap && prefix && rows && sorted_coords, "comb_index_rank_scatter: null pointer");
+  index_rank_kernel<<<cdiv(n_max, 256), 256, 0, stream>>>((const int4*)coords, n_max, n_dev, batch, D, H, W,
+                                                          (const uint32_t*)bitmap, (const int*)prefix, rows,
+                                                          (int4*)sorted_coords, sorted_cap);
   COMB_LAUNCH_CHECK();
   return COMB_OK;
 }

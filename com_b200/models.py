@@ -230,8 +230,10 @@ class VoxelResBackBone8x(nn.Module):
         steps = []          # per level: dict(coords, count, shape, nbr, ev_nbr, nbr_d, ev_d)
         with torch.cuda.stream(side):
             shape = list(self.sparse_shape)
-            idx = ops.index_build(coords.contiguous(), batch_size, shape, n_dev=n_dev)
-            perm = ops.index_rank(coords, idx, n_dev=n_dev)
+            # level 1: the voxel list is unique, so its rows in key order come from the rank of every voxel (scatter)
+            # rather than from enumerating the 46 MB bitmap
+            idx = ops.index_build(coords.contiguous(), batch_size, shape, n_dev=n_dev, want_coords=False)
+            perm, _ = ops.index_rank(coords, idx, n_dev=n_dev, scatter_coords=True)
             ev_perm = handoff(perm, idx.coords, idx.count)
             cur_coords, cur_n = idx.coords, idx.count
             convs = {2: plan['down2'], 3: plan['down3'], 4: plan['down4'], 5: plan['out']}

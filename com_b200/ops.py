@@ -247,13 +247,22 @@ def index_build(coords, batch, shape, conv=None, out_cap=None, n_dev=None, want_
     return GridIndex(bitmap, prefix, batch, shape, out, cnt)
 
 
-def index_rank(coords, index, n_dev=None):
-    """Row of every coordinate in the index (-1 when absent)."""
+def index_rank(coords, index, n_dev=None, scatter_coords=False):
+    """Row of every coordinate in the index (-1 when absent).  scatter_coords=True (unique coords, e.g. a voxel list
+    indexed with want_coords=False): also returns the coordinate list in key order, and stores it in index.coords."""
     lib = _lib.load()
     _need(coords, torch.int32, "coords")
     n = int(coords.shape[0])
     rows = torch.empty((n,), dtype=torch.int32, device=coords.device)
     D, H, W = index.shape
+    if scatter_coords:
+        sorted_coords = torch.empty((max(n, 1), 4), dtype=torch.int32, device=coords.device)
+        with _Scope("index_rank", n=n):
+            check(lib.comb_index_rank_scatter(_p(coords), n, _p(n_dev), index.batch, D, H, W, _p(index.bitmap),
+                                              _p(index.prefix), _p(rows), _p(sorted_coords), n, _stream()),
+                  "comb_index_rank_scatter")
+        index.coords = sorted_coords
+        return rows, sorted_coords
     with _Scope("index_rank", n=n):
         check(lib.comb_index_rank(_p(coords), n, _p(n_dev), index.batch, D, H, W, _p(index.bitmap), _p(index.prefix),
                                   _p(rows), _stream()), "comb_index_rank")

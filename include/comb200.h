@@ -141,6 +141,9 @@ int comb_nbrmap_to_pairs(const int* nbr, int K, int no_max, const int* no_dev, i
  *   bitmap [comb_index_bitmap_bytes], prefix [comb_index_prefix_bytes]; out_coords (nullable)
  *   [out_cap,4] receives the rows in key order, out_count (device int) their number (clamped to out_cap).
  * comb_index_rank: rows[i] = row of coords[i] in the index, -1 if absent (voxel order -> key order).
+ * comb_index_rank_scatter: comb_index_rank that ALSO writes sorted_coords[rows[i]] = coords[i] — for UNIQUE coords
+ *   (a voxel list) this is the row list in key order without enumerating the bitmap (build the index with
+ *   out_coords == NULL, which then only finalises the block prefixes).
  * comb_nbrmap_build_indexed: same contract as comb_nbrmap_build with the index of the INPUT level. */
 size_t comb_index_bitmap_bytes(int batch, int D, int H, int W);
 size_t comb_index_prefix_bytes(int batch, int D, int H, int W);
@@ -149,6 +152,9 @@ int comb_index_build(const int* coords, int n_max, const int* n_dev, int batch, 
                      void* bitmap, void* prefix, int* out_coords, int out_cap, int* out_count, void* stream);
 int comb_index_rank(const int* coords, int n_max, const int* n_dev, int batch, int D, int H, int W,
                     const void* bitmap, const void* prefix, int* rows, void* stream);
+int comb_index_rank_scatter(const int* coords, int n_max, const int* n_dev, int batch, int D, int H, int W,
+                            const void* bitmap, const void* prefix, int* rows, int* sorted_coords,
+                            int sorted_cap, void* stream);
 int comb_nbrmap_build_indexed(const int* out_coords, int no_max, const int* no_dev,
                               const void* bitmap, const void* prefix, int batch, int iD, int iH, int iW,
                               const int* ksize, const int* stride, const int* pad, const int* dil,

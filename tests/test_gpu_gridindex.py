@@ -117,3 +117,27 @@ def test_waymo_frame_full_size():
     assert n2 == len(want) and np.array_equal(o2.coords[:n2].cpu().numpy(), want)
     nbr2 = ops.nbrmap_build_indexed(o2.coords[:n2].contiguous(), idx, ks, st, pd, dl)
     assert np.array_equal(nbr2.cpu().numpy(), oracle.nbrmap(want, sc, shape, ks, st, pd, dl))
+
+
+def test_rank_scatter_gives_key_ordered_rows_without_emit():
+    """Level-1 path of the fused backbone: index built WITHOUT coordinate emission (prefix finalisation only), rows in
+    key order produced by comb_index_rank_scatter from the (unique) voxel list — same rows, same ranks as the emit path,
+    incl. a device-side row count smaller than the buffer."""
+    rng = np.random.default_rng(8)
+    batch, shape = 2, [21, 90, 77]
+    coords = random_coords(rng, 20000, batch, shape)
+    full = ops.index_build(cuda(coords), batch, shape)
+    lean = ops.index_build(cuda(coords), batch, shape, want_coords=False)
+    rows, sorted_c = ops.index_rank(cuda(coords), lean, scatter_coords=True)
+    n = int(lean.count)
+    assert n == int(full.count) == len(coords)
+    assert torch.equal(sorted_c[:n], full.coords[:n])
+    assert torch.equal(rows, ops.index_rank(cuda(coords), full))
+    nblk = (batch * 21 * 90 * 77 + 255) // 256          # rank blocks that hold cells: their global prefixes agree
+    assert torch.equal(lean.prefix.view(torch.int32)[:nblk], full.prefix.view(torch.int32)[:nblk])
+    nd = torch.tensor([12345], dtype=torch.int32, device="cuda")
+    lean2 = ops.index_build(cuda(coords), batch, shape, want_coords=False, n_dev=nd)
+    rows2, sorted2 = ops.index_rank(cuda(coords), lean2, n_dev=nd, scatter_coords=True)
+    ref2 = ops.index_build(cuda(coords[:12345]), batch, shape)
+    assert int(lean2.count) == 12345 and torch.equal(sorted2[:12345], ref2.coords[:12345])
+    assert torch.equal(rows2[:12345], ops.index_rank(cuda(coords[:12345]), ref2))
