@@ -56,10 +56,14 @@ __device__ __forceinline__ bool point_key(const float* __restrict__ p, const Vox
 
 __global__ void __launch_bounds__(256) vox_insert_kernel(const float* __restrict__ points, Frames fr, int C, VoxGeom g,
                                                           int T, uint32_t* __restrict__ keys, int* __restrict__ cand,
-                                                          uint32_t mask, int* __restrict__ slot_of_point) {
-  const int frame = blockIdx.y;
-  const int i = fr.at(frame) + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= fr.at(frame + 1)) return;
+                                                          uint32_t mask, int* __restrict__ slot_of_point, int batch) {
+  // one thread per point of the concatenated cloud; its frame = the last offset <= i (batch <= 32: linear search).
+  // (A (points-per-frame, batch) grid sized for the worst case "one frame holds every point" launches batch x more
+  // blocks than there are points when the offsets live on the device.)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= fr.at(batch)) return;
+  int frame = 0;
+  while (frame + 1 < batch && i >= fr.at(frame + 1)) ++frame;
   const float* p = points + (size_t)i * C;
   float xyz[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
   uint32_t key;
@@ -404,8 +408,8 @@ extern "C" int comb_voxelize(const float* points, const int* frame_offsets_host,
   COMB_CUDA(cudaMemsetAsync(w.cand, 0x7F, (size_t)w.slots * max_points * 4, stream));
   const int T = max_points;
   if (max_frame > 0) {
-    dim3 gi(cdiv(max_frame, 256), batch);
-    vox_insert_kernel<<<gi, 256, 0, stream>>>(points, fr, C, g, T, w.keys, w.cand, w.slots - 1, w.slot_of_point);
+    vox_insert_kernel<<<cdiv(n_total, 256), 256, 0, stream>>>(points, fr, C, g, T, w.keys, w.cand, w.slots - 1,
+                                                              w.slot_of_point, batch);
     COMB_LAUNCH_CHECK();
     dim3 gc(cdiv(max_frame, kChunk), batch);
     vox_count_kernel<<<gc, kChunk, 0, stream>>>(fr, T, w.cand, w.slot_of_point, w.chunk_counts, w.chunks_per_frame);
