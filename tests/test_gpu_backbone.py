@@ -284,3 +284,36 @@ def test_backbone_forward_backward_train_mode(setup):
         tol = 1e-2 if smooth else 0.15
         for name, an, fds in report:
             assert abs(fds[0] - an) <= tol * max(abs(fds[0]), abs(an)) + 1e-3, (smooth, report)
+
+
+def test_multisweep_six_channel_pipeline():
+    """BASELINE configs[4] shape of the input: aggregated sweeps carry a 6th (timestamp) channel
+    (waymo_dataset_multiframe.yaml).  The fused bf16 pipeline with input_channels=6 agrees with the module path in
+    fp32 check arithmetic (same weights) on every level: indices bit-exact up to the row order, features 2e-2."""
+    frames = [synth.make_small_cloud(n, seed=s, extent=(25.0, 25.0, 4.0), channels=6) for s, n in ((21, 26000), (22, 19000))]
+    for f in frames:
+        f[:, 2] *= 0.4
+        f[:, 5] = np.floor(f[:, 5] * 3) * 0.1          # timestamps {0, 0.1, 0.2}-like
+    pipe = pipeline.FramePipeline(input_channels=6, point_cloud_range=RANGE, voxel_size=VSIZE, max_voxels=40000, seed=5)
+    randomize_bn(pipe.backbone, 6)
+    fused = pipe.forward_host(frames)
+    offs = [0, len(frames[0]), len(frames[0]) + len(frames[1])]
+    r = ops.voxelize(torch.from_numpy(np.concatenate(frames)).cuda(), offs, VSIZE, RANGE, 5, 40000)
+    m = int(r["counts"][2])
+    bd = models.MeanVFE(None, 6)({"batch_size": 2, "voxels": r["voxels"][:m], "voxel_num_points": r["num_points"][:m],
+                                  "voxel_coords": r["coords"][:m].float()})
+    pipe.backbone.fused = False
+    try:
+        with torch.no_grad():
+            bd = pipe.backbone(bd)
+    finally:
+        pipe.backbone.fused = True
+    names = ["x_conv1", "x_conv2", "x_conv3", "x_conv4"]
+    got = [fused["multi_scale_3d_features"][n] for n in names] + [fused["encoded_spconv_tensor"]]
+    want = [bd["multi_scale_3d_features"][n] for n in names] + [bd["encoded_spconv_tensor"]]
+    for g, w in zip(got, want):
+        wc, wf = w.indices.cpu().numpy(), w.features.cpu().numpy()
+        o = key_order(wc, w.spatial_shape)
+        assert g.spatial_shape == w.spatial_shape and np.array_equal(g.indices.cpu().numpy(), wc[o])
+        assert rel_err(g.features.float().cpu().numpy(), wf[o].astype(np.float64)) < 2e-2
+    assert got[-1].features.shape[0] > 100
