@@ -388,38 +388,48 @@ def ours(args):
         c["n"] += 1
 
     # ---- e2e: public API with HOST buffers: pinned points in, encoded tensor + counts back to pinned host, every step.
-    # FrameStream is the serving loop (double buffered: the H2D of step k+1 and the D2H of step k-1 overlap the kernels
-    # of step k); all copies of all K steps happen inside the timed region, which ends when the last result has landed.
-    # The L2 flush between steps runs on the launch stream; its own event-measured time is subtracted.
+    # FrameStream is the serving loop: two lanes (two captured step graphs) so that the H2D + voxelizer + level-1 index
+    # of step k+1 run while the convolutions of step k are in flight, D2H of step k-1 on a copy-out stream; all copies
+    # of all K steps happen inside the timed region, which ends when the last result has landed.
+    # L2: no flush here — every step reads a DIFFERENT pinned input (a ring of distinct batches larger than the 126 MB
+    # L2 in total, delivered by H2D) and streams ~0.4 GB of intermediates.
+    n_ring = 10                                              # 10 x 13.6 MB of inputs > 126 MB
+    ring = []
+    for j in range(n_ring):
+        # same frames, different content order: frames rolled by j, points of every frame cyclically shifted
+        fr = [np.roll(frames[(b + j) % BATCH], 1237 * j, axis=0) for b in range(BATCH)]
+        o = np.concatenate([[0], np.cumsum([len(f) for f in fr])]).astype(int).tolist()
+        ring.append((torch.from_numpy(np.concatenate(fr, axis=0)).pin_memory(), o))
     stream = pipeline.FrameStream(pipe, host, offs)
-    for _ in range(3):
-        stream.result(stream.submit(host, offs))
+    for j in range(4):
+        stream.result(stream.submit(*ring[j % n_ring]))
     torch.cuda.synchronize()
     cdist.barrier()
-    fl_evs = []
+    launches_e2e0 = stream.graph_launches
     t_wall0 = time.perf_counter()
     e0 = torch.cuda.Event(enable_timing=True)
     e0.record()
+    for lane in stream.lanes:
+        lane["launch"].wait_event(e0)
+    stream.s_in.wait_event(e0)
     prev = None
-    for _ in range(args.steps):
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        flush.fill_(1)
-        f1.record()
-        fl_evs.append((f0, f1))
-        tk = stream.submit(host, offs)
+    rows_seen = set()
+    for k in range(args.steps):
+        tk = stream.submit(*ring[k % n_ring])
         if prev is not None:
-            res = stream.result(prev)
+            rows_seen.add(stream.result(prev)["rows"])
         prev = tk
-    res = stream.result(prev)                 # the caller owns the last result: every D2H has landed
-    e_last = stream.done_event(prev)
+    rows_seen.add(stream.result(prev)["rows"])       # the caller owns the last result: every D2H has landed
+    e_last = torch.cuda.Event(enable_timing=True)
+    for tk in range(max(0, stream.k - stream.LANES), stream.k):
+        stream.s_out.wait_event(stream.done_event(tk))
+    e_last.record(stream.s_out)
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
-    t_flush = sum(a.elapsed_time(b) for a, b in fl_evs) / 1e3
-    t_e2e = e0.elapsed_time(e_last) / 1e3 - t_flush
+    t_e2e = e0.elapsed_time(e_last) / 1e3
     d2h = stream.d2h_bytes
     h2d = stream.h2d_bytes
-    assert res["rows"] == enc_rows, "streamed result differs from the synchronous one"
+    assert rows_seen == {enc_rows}, "streamed results differ from the synchronous one: %s vs %d" % (rows_seen, enc_rows)
     cdist.barrier()
     clocks = sampler.stop()
 
@@ -477,9 +487,11 @@ def ours(args):
                        "l2": "flushed between steps (512 MiB write outside the timed window)"},
             "e2e": {"value": total_frames / t_e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e_max / args.steps,
-                    "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
-                    "l2_flush_ms_per_step_subtracted": 1e3 * t_flush / args.steps,
-                    "api": "FrameStream.submit/result (double buffered: copies of neighbouring steps overlap the kernels)",
+                    "wall_ms_per_step": 1e3 * t_wall / args.steps,
+                    "l2": "no flush: a ring of %d distinct pinned input batches (%.0f MB > L2) delivered by H2D" % (
+                        n_ring, n_ring * host.numel() * 4 / 1e6),
+                    "api": "FrameStream.submit/result (two lanes = two step graphs in flight; H2D, kernels and D2H of "
+                           "neighbouring steps overlap)",
                     "result": "encoded_spconv_tensor (features bf16 + indices, capacity-sized) + all row counts to pinned "
                               "host; the dense BEV tensor is produced on the device"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
