@@ -237,19 +237,22 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
     const bool tr = q == 0 && grp == 0 && lane == 0;
     int s = 0, gst = 0;
     uint32_t ph = 0;
+    const int t = grp & (T - 1);          // chunk slot x = 4*st + grp of a stage belongs to row tile x & 1 = grp & 1
     for (int it = 0; it < my_super; ++it) {
+      // per pass: this warp's tile, its index buffer (waited for once), whether the tile exists
+      const int n = (it << lT) + t;                    // tile sequence number of this CTA
+      const int buf = n & (NI - 1);
+      const bool absent = t == 1 && (int)blockIdx.x + it * (int)gridDim.x >= nfull;
+      const uint32_t idx_tile = idx_base + (uint32_t)buf * idx_buf_bytes;
+      mbar_wait_sleep(bars + kBarIdx + 8 * buf, (uint32_t)(n >> lNI) & 1u);   // also for an absent tile: its fill must have landed before the buffer is handed back
       for (int st = 0; st < nst; ++st, ++gst) {
-        const int x = st * 4 + grp;
-        const bool have = x < CT && !((x & (T - 1)) == 1 && (int)blockIdx.x + it * (int)gridDim.x >= nfull);
+        const int c = 2 * st + (grp >> 1);             // x >> 1
+        const bool have = c < nchunks && !absent;
         uint4 v[2][2][2];     // [16-lane half][row, row+8][piece]
         if (TRACE && tr) dbg_stamp(p.dbg, gst, 2);
         if (have) {
-          const int c = x >> lT, t = x & (T - 1);
-          const int n = (it << lT) + t;                  // tile sequence number of this CTA
-          const int buf = n & (NI - 1);
-          mbar_wait_sleep(bars + kBarIdx + 8 * buf, (uint32_t)(n >> lNI) & 1u);
           if (TRACE && tr) dbg_stamp(p.dbg, gst, 7);
-          const uint32_t idx_c = idx_base + (uint32_t)buf * idx_buf_bytes +
+          const uint32_t idx_c = idx_tile +
                                  (uint32_t)(CIN <= 64 ? c * Cfg::kOffPerChunk : c / Cfg::kChunksPerOff) * kBM * 4;
           const int ehalf = CIN > 64 ? (c % Cfg::kChunksPerOff) * 64 : 0;
 #pragma unroll
