@@ -270,6 +270,81 @@ def reference_arm(args):
     }))
 
 
+# ------------------------------------------------------------------------------------------- box ops (configs[0])
+def box_ops_leg(torch, frame, peaks):
+    """BASELINE configs[0] (the reference's CPU-runnable case) for rows a11-a16: points_in_boxes on a 180k-point frame
+    x 500 boxes, rotated BEV IoU 500 x 500 and NMS of 500 boxes — our kernels (CUDA events, 20 repetitions each, the
+    360 MB mask output is larger than L2) and, beside them, the reference's own C++ (oracle/_ref compiled from
+    /root/reference; the oracle port when that build is absent) on one host core (it is single-threaded by
+    construction)."""
+    import oracle
+    from com_b200 import ops, synth
+    from oracle import build_ref
+    dev = torch.device("cuda", torch.cuda.current_device())
+    pts_np = np.ascontiguousarray(frame[:, :3])
+    boxes_np = synth.make_boxes(500, seed=0)
+    boxes_np[:, 2] = -1.0
+    cl_np = synth.make_clustered_boxes(500, seed=21)
+    pts, boxes, cl = torch.from_numpy(pts_np).to(dev), torch.from_numpy(boxes_np).to(dev), torch.from_numpy(cl_np).to(dev)
+    trig = torch.from_numpy(ops.box_trig_host(boxes_np)).to(dev)
+    trig4 = torch.from_numpy(ops.box_trig4_host(cl_np)).to(dev)
+    P, nb = int(pts.shape[0]), 500
+    mask = torch.empty((nb, P), dtype=torch.int32, device=dev)
+    iou = torch.empty((nb, nb), dtype=torch.float32, device=dev)
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        torch.cuda._sleep(10_000_000)      # park the stream (~5 ms) so that all launches are queued: device time, not host time
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms_pib = timed(lambda: ops.points_in_boxes_mask(pts, boxes, trig, out=mask))
+    ms_iou = timed(lambda: ops.boxes_bev(cl, cl, flavour="cpu", what="iou", trig_a=trig4, trig_b=trig4, out=iou))
+    ms_nms = timed(lambda: ops.nms(cl, 0.7, rotated=True, flavour="gpu", trig=trig4))
+    by_pib = P * 12.0 + nb * 28.0 + nb * P * 4.0
+    by_iou = 2 * nb * 28.0 + nb * nb * 4.0
+    out = {"workload": "configs[0]: %d points x %d boxes points_in_boxes, %dx%d rotated BEV IoU, NMS of %d boxes (thresh 0.7)" % (
+               P, nb, nb, nb, nb),
+           "points_in_boxes": {"ms": ms_pib, "achieved_gbs": by_pib / ms_pib / 1e6, "frac_of_hbm_peak": by_pib / ms_pib / 1e6 / peaks["hbm"],
+                               "bound": "hbm (mask write)"},
+           "bev_iou": {"ms": ms_iou, "pairs_per_us": nb * nb / ms_iou / 1e3, "achieved_gbs": by_iou / ms_iou / 1e6,
+                       "bound": "SFU / latency (1 MB output)"},
+           "nms": {"ms": ms_nms, "bound": "latency (mask + one-warp sweep on the device, no host round trip)"}}
+    # reference CPU path beside it
+    kind = "port"
+    try:
+        if build_ref.available():
+            roi, i3d = build_ref.load_ref("ref_roiaware_pool3d_cuda"), build_ref.load_ref("ref_iou3d_nms_cuda")
+            kind = "reference"
+    except Exception:
+        kind = "port"
+    t0 = time.perf_counter()
+    if kind == "reference":
+        o = torch.zeros((nb, P), dtype=torch.int32)
+        roi.points_in_boxes_cpu(torch.from_numpy(boxes_np), torch.from_numpy(pts_np), o)
+    else:
+        oracle.points_in_boxes_cpu(pts_np, boxes_np)
+    t1 = time.perf_counter()
+    if kind == "reference":
+        o2 = torch.zeros((nb, nb), dtype=torch.float32)
+        i3d.boxes_iou_bev_cpu(torch.from_numpy(cl_np), torch.from_numpy(cl_np), o2)
+    else:
+        oracle.boxes_bev_cpu(cl_np, cl_np)
+    t2 = time.perf_counter()
+    oracle.nms_cpu(cl_np, 0.7)        # IoU matrix + greedy sweep (the reference has no CPU NMS entry point)
+    t3 = time.perf_counter()
+    out["cpu"] = {"kind": kind, "cores": 1, "points_in_boxes_ms": 1e3 * (t1 - t0), "bev_iou_ms": 1e3 * (t2 - t1),
+                  "nms_ms_port": 1e3 * (t3 - t2)}
+    return out
+
+
 # ------------------------------------------------------------------------------------------- GPU arm
 def ours(args):
     import torch
@@ -537,6 +612,11 @@ def ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_cpu:
+            try:
+                line["box_ops"] = box_ops_leg(torch, frames[0], peaks)
+            except Exception as e:       # the secondary leg must never take the headline line down
+                line["box_ops"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line))
     cdist.barrier()
     return line
