@@ -9,16 +9,18 @@ from com_b200 import pipeline
 frames = bench.make_frames([1000 + b for b in range(4)])
 offs = np.concatenate([[0], np.cumsum([len(f) for f in frames])]).astype(int).tolist()
 pts = torch.from_numpy(np.concatenate(frames, axis=0)).cuda()
-pipes = [pipeline.FramePipeline(seed=0, use_graph=True) for _ in range(2)]
-pipes[1].backbone = pipes[0].backbone
-streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+NL = 4
+pipes = [pipeline.FramePipeline(seed=0, use_graph=True)]
+for _ in range(NL - 1):
+    pipes.append(pipes[0].clone_lane())
+streams = [torch.cuda.Stream() for _ in range(NL)]
 for p, s in zip(pipes, streams):
     with torch.cuda.stream(s):
         for _ in range(3):
             p.forward_device(pts, offs)
 torch.cuda.synchronize()
 K = 40
-for lanes in (1, 2, 1, 2):
+for lanes in (1, 2, 3, 4, 2, 3):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
