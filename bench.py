@@ -345,6 +345,49 @@ def box_ops_leg(torch, frame, peaks):
     return out
 
 
+# ------------------------------------------------------------------------------------------- training leg (configs[2])
+def train_leg(torch, frames):
+    """BASELINE configs[2], the part of a training step that is on this path (row a8): VoxelResBackBone8x in TRAIN mode
+    (module path: fp32 sparse convs with autograd — dgrad through transposed rulebooks, wgrad — BatchNorm1d batch
+    statistics), forward + backward + SGD step on a batch of 2 frames.  fp32 check arithmetic on CUDA cores: a
+    correctness path, not yet a tensor-core one."""
+    from com_b200 import models, ops, synth
+    dev = torch.device("cuda", torch.cuda.current_device())
+    fr = frames[:2]
+    offs = np.concatenate([[0], np.cumsum([len(f) for f in fr])]).astype(int).tolist()
+    pts = torch.from_numpy(np.concatenate(fr, axis=0)).to(dev)
+    torch.manual_seed(0)
+    net = models.VoxelResBackBone8x(None, 5, synth.GRID_SIZE).to(dev).train()
+    net.fused = False
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3)
+
+    def step():
+        r = ops.voxelize(pts, offs, synth.VOXEL_SIZE, synth.POINT_CLOUD_RANGE, synth.MAX_POINTS_PER_VOXEL,
+                         synth.MAX_NUMBER_OF_VOXELS)
+        m = int(r["counts"][2])
+        bd = models.MeanVFE(None, 5)({"voxels": r["voxels"][:m], "voxel_num_points": r["num_points"][:m]})
+        bd = net({"batch_size": 2, "voxel_features": bd["voxel_features"], "voxel_coords": r["coords"][:m].float()})
+        loss = bd["encoded_spconv_tensor"].features.float().square().mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 3
+    for _ in range(reps):
+        last = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"workload": "configs[2], sparse part: voxelize + VoxelResBackBone8x train-mode forward + backward + SGD step, "
+                        "batch 2, fp32 check arithmetic (module path)", "ms_per_step": ms, "frames_per_s": 2e3 / ms,
+            "loss_finite": bool(np.isfinite(last))}
+
+
 # ------------------------------------------------------------------------------------------- GPU arm
 def ours(args):
     import torch
@@ -619,6 +662,10 @@ def ours(args):
                 line["box_ops"] = box_ops_leg(torch, frames[0], peaks)
             except Exception as e:       # the secondary leg must never take the headline line down
                 line["box_ops"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            try:
+                line["train_sparse_part"] = train_leg(torch, frames)
+            except Exception as e:
+                line["train_sparse_part"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line))
     cdist.barrier()
     return line
