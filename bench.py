@@ -373,19 +373,27 @@ def train_leg(torch, frames):
         opt.step()
         return float(loss.detach())
 
-    step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    reps = 3
-    for _ in range(reps):
-        last = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    return {"workload": "configs[2], sparse part: voxelize + VoxelResBackBone8x train-mode forward + backward + SGD step, "
-                        "batch 2, fp32 check arithmetic (module path)", "ms_per_step": ms, "frames_per_s": 2e3 / ms,
-            "loss_finite": bool(np.isfinite(last))}
+    from com_b200 import sparse
+    res = {"workload": "configs[2], sparse part: voxelize + VoxelResBackBone8x train-mode forward + backward + SGD step, "
+                       "batch 2 (module path with autograd)"}
+    old = sparse.config.compute
+    try:
+        for mode, label in (("f32", "fp32_check"), ("bf16", "bf16_fwd_dgrad_tcgen05")):
+            sparse.config.compute = mode
+            step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            reps = 3
+            for _ in range(reps):
+                last = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            res[label] = {"ms_per_step": ms, "frames_per_s": 2e3 / ms, "loss_finite": bool(np.isfinite(last))}
+    finally:
+        sparse.config.compute = old
+    return res
 
 
 # ------------------------------------------------------------------------------------------- GPU arm

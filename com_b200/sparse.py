@@ -20,7 +20,9 @@ from . import ops
 
 class _Config:
     # "f32": fp32 check mode (CUDA cores, reference-exact layout of the sum);
-    # "bf16": tensor-core path (bf16 operands, fp32 accumulate) for no-grad forward passes.
+    # "bf16": tensor-core path (bf16 operands, fp32 accumulate): no-grad forward passes, and — with autograd — forward
+    #         and dgrad on the tcgen05 kernel (dgrad = the same gather-GEMM over the transposed rulebook with W^T),
+    #         wgrad on the fp32 kernel.
     compute = os.environ.get("COMB200_COMPUTE", "f32")
 
 
@@ -201,6 +203,45 @@ class _SpConvFunction(torch.autograd.Function):
         return din, dw, db, None, None, None
 
 
+class _SpConvFunctionBF16(torch.autograd.Function):
+    """Mixed-precision training form (config.compute == "bf16"): forward and dgrad run the tcgen05 gather-GEMM with
+    bf16 operands and fp32 accumulation — dgrad is the SAME kernel over the transposed rulebook with the transposed
+    weights, din[i] = sum_k dout[nbr_t[k][i]] @ W[:,k,:] — and wgrad stays on the fp32 kernel (fp32 features and
+    gradients).  Outputs and gradients are fp32 tensors."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, bias, rb, gather_map, scatter_map_fn):
+        Cout, Cin = weight.shape[0], weight.shape[-1]
+        w3 = weight.detach().reshape(Cout, -1, Cin).contiguous().float()
+        feats = feats.contiguous()
+        xb = ops.cast_pad(feats, ops.pad16(Cin))
+        out = ops.spconv_fwd_bf16(xb, ops.pack_weight_bf16(w3), int(w3.shape[1]), Cout, gather_map,
+                                  bias=bias.detach().float() if bias is not None else None, out_dtype=torch.float32)
+        ctx.save_for_backward(feats, weight)
+        ctx.gather_map, ctx.scatter_map_fn, ctx.has_bias = gather_map, scatter_map_fn, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        feats, weight = ctx.saved_tensors
+        Cout, Cin = weight.shape[0], weight.shape[-1]
+        w3 = weight.detach().reshape(Cout, -1, Cin).contiguous().float()
+        K = int(w3.shape[1])
+        dout = dout.contiguous().float()
+        din = dw = db = None
+        if ctx.needs_input_grad[0]:
+            cin_p = ops.pad16(Cin)                       # the kernel's N must be 16 / 32 / 64 / 128: zero rows beyond Cin
+            wt = torch.zeros((cin_p, K, Cout), dtype=torch.float32, device=w3.device)
+            wt[:Cin] = w3.permute(2, 1, 0)
+            din = ops.spconv_fwd_bf16(ops.cast_pad(dout, Cout), ops.pack_weight_bf16(wt), K, cin_p, ctx.scatter_map_fn(),
+                                      out_dtype=torch.float32)[:, :Cin].contiguous()
+        if ctx.needs_input_grad[1]:
+            dw = ops.spconv_wgrad_f32(feats, dout, ctx.gather_map).reshape(weight.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dout.sum(0)
+        return din, dw, db, None, None, None
+
+
 class SparseConvolution(SparseModule):
     """Mirror of spconv.pytorch.conv.SparseConvolution for ndim=3."""
 
@@ -315,6 +356,9 @@ class SparseConvolution(SparseModule):
             bias = self.bias.detach().float() if self.bias is not None else None
             out = ops.spconv_fwd_bf16(xb, self._packed_weight(), K, self.out_channels, gather_map, bias=bias,
                                       out_dtype=feats.dtype if feats.dtype == torch.bfloat16 else torch.float32)
+        elif needs_grad and config.compute == "bf16" and self.out_channels in (16, 32, 64, 128) \
+                and ops.pad16(self.in_channels) in (16, 32, 64, 128):
+            out = _SpConvFunctionBF16.apply(feats.float(), self.weight, self.bias, rb, gather_map, scatter_fn)
         else:
             out = _SpConvFunction.apply(feats.float(), self.weight, self.bias, rb, gather_map, scatter_fn)
         res = SparseConvTensor(out, out_indices, out_shape, input.batch_size, input.grid, input.voxel_num,

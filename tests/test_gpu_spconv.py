@@ -189,3 +189,31 @@ print("alt-ok")
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, PYTHONPATH=root, **env),
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "alt-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("Cin,Cout,subm", [(5, 16, True), (16, 32, False), (64, 64, True), (128, 128, False)])
+def test_module_autograd_bf16_training_form(Cin, Cout, subm):
+    """config.compute = "bf16" with autograd: forward and dgrad on the tcgen05 kernel (dgrad = the same gather-GEMM over
+    the transposed rulebook with W^T), wgrad on the fp32 kernel.  vs the oracle: 2e-2 for the bf16-operand results
+    (forward, dgrad), 1e-4 for wgrad and the bias gradient (fp32 arithmetic on fp32 operands)."""
+    st = (1, 1, 1) if subm else (2, 2, 2)
+    coords, out_coords, nbr, feats, W, rng = make_case(Cin * 3 + Cout, 2500, Cin, Cout, st=st, subm=subm)
+    mod = (sparse.SubMConv3d(Cin, Cout, 3, bias=True, indice_key="k") if subm else
+           sparse.SparseConv3d(Cin, Cout, 3, stride=2, padding=1, bias=True, indice_key="k")).cuda()
+    with torch.no_grad():
+        mod.weight.copy_(cuda(W).reshape(Cout, 3, 3, 3, Cin))
+    bias = mod.bias.detach().cpu().numpy()
+    old = sparse.config.compute
+    sparse.config.compute = "bf16"
+    try:
+        x = cuda(feats).requires_grad_(True)
+        y = mod(sparse.SparseConvTensor(x, cuda(coords), [12, 40, 40], 2))
+        dout = rng.normal(size=tuple(y.features.shape)).astype(np.float32)
+        y.features.backward(cuda(dout))
+    finally:
+        sparse.config.compute = old
+    assert y.features.dtype == torch.float32 and x.grad.dtype == torch.float32
+    assert rel_err(y.features.detach().cpu().numpy(), oracle.conv_fwd(feats, W, nbr, bias)) < TOL_BF16
+    assert rel_err(x.grad.cpu().numpy(), oracle.conv_dgrad(dout, W, nbr, len(coords))) < TOL_BF16
+    assert rel_err(mod.weight.grad.reshape(Cout, 27, Cin).cpu().numpy(), oracle.conv_wgrad(feats, dout, nbr)) < TOL_F32
+    assert rel_err(mod.bias.grad.cpu().numpy(), dout.sum(0)) < TOL_F32
