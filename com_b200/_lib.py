@@ -53,6 +53,8 @@ SIGNATURES = {
     "comb_spconv_pack_weight_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "comb_spconv_fwd_bf16": (c_int, [_P, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P,
                                      c_int, _P]),
+    "comb_spconv_wgrad_bf16_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "comb_spconv_wgrad_bf16": (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "comb_debug_conv_trace": (c_int, [_P]),
     "comb_affine_relu": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, _P, c_int, _P, _P]),
     "comb_cast_pad": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P]),

@@ -14,7 +14,7 @@ from ._lib import DT_BF16, DT_F32, EPI_AFFINE, EPI_BIAS, EPI_RELU, EPI_RESIDUAL,
 
 __all__ = [
     "voxelize", "mean_vfe", "hash_build", "conv_out_coords", "conv_out_shape", "nbrmap_build",
-    "nbrmap_transpose", "nbrmap_to_pairs", "spconv_fwd_f32", "spconv_dgrad_f32", "spconv_wgrad_f32",
+    "nbrmap_transpose", "nbrmap_to_pairs", "spconv_fwd_f32", "spconv_dgrad_f32", "spconv_wgrad_f32", "spconv_wgrad_bf16",
     "pack_weight_bf16", "spconv_fwd_bf16", "affine_relu", "cast_pad", "dense", "points_in_boxes_mask",
     "points_in_boxes_index", "boxes_bev", "nms", "box_trig_host", "box_trig4_host",
 ]
@@ -358,6 +358,26 @@ def spconv_wgrad_f32(feats, dout, nbr, no_dev=None):
     dw = torch.empty((Cout, K, Cin), dtype=torch.float32, device=feats.device)
     check(lib.comb_spconv_wgrad_f32(_p(feats), Cin, _p(dout), Cout, K, _p(nbr), ld, int(dout.shape[0]), _p(no_dev),
                                     _p(dw), _stream()), "comb_spconv_wgrad_f32")
+    return dw
+
+
+def spconv_wgrad_bf16(feats, dout, nbr, Cin, no_dev=None):
+    """Tensor-core wgrad: feats (Ni, Cin_p) bf16 (zero padded beyond Cin), dout (No, Cout) bf16 -> dW (Cout, K, Cin)
+    fp32 (bf16 products, fp32 accumulation in tensor memory, deterministic reduction over the row chunks)."""
+    lib = _lib.load()
+    _need(feats, torch.bfloat16, "feats")
+    _need(dout, torch.bfloat16, "dout")
+    _need(nbr, torch.int32, "nbr")
+    K, ld = int(nbr.shape[0]), int(nbr.shape[1])
+    cin_p, Cout, Cin, no = int(feats.shape[1]), int(dout.shape[1]), int(Cin), int(dout.shape[0])
+    nbytes = lib.comb_spconv_wgrad_bf16_workspace_bytes(cin_p, Cin, Cout, K, no)
+    if nbytes == 0:
+        raise RuntimeError("unsupported conv shape for the bf16 wgrad: Cin_p=%d Cin=%d Cout=%d K=%d" % (cin_p, Cin, Cout, K))
+    ws = _ws(nbytes, feats.device)
+    dw = torch.empty((Cout, K, Cin), dtype=torch.float32, device=feats.device)
+    with _Scope("spconv_wgrad_bf16", cin=cin_p, cout=Cout, K=K, nbr=nbr, no=no, no_dev=no_dev, ni=int(feats.shape[0])):
+        check(lib.comb_spconv_wgrad_bf16(_p(feats), cin_p, Cin, _p(dout), Cout, K, _p(nbr), ld, no, _p(no_dev), _p(dw),
+                                         _p(ws), nbytes, _stream()), "comb_spconv_wgrad_bf16")
     return dw
 
 

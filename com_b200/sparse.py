@@ -21,9 +21,10 @@ from . import ops
 class _Config:
     # "f32": fp32 check mode (CUDA cores, reference-exact layout of the sum);
     # "bf16": tensor-core path (bf16 operands, fp32 accumulate): no-grad forward passes, and — with autograd — forward
-    #         and dgrad on the tcgen05 kernel (dgrad = the same gather-GEMM over the transposed rulebook with W^T),
-    #         wgrad on the fp32 kernel.
+    #         dgrad (the same gather-GEMM over the transposed rulebook with W^T) and wgrad on the tcgen05 kernels.
     compute = os.environ.get("COMB200_COMPUTE", "f32")
+    # wgrad of the "bf16" training form: "bf16" = tcgen05 kernel (conv_wgrad.cu), "f32" = fp32 check kernel
+    wgrad = os.environ.get("COMB200_WGRAD", "bf16")
 
 
 config = _Config()
@@ -204,10 +205,12 @@ class _SpConvFunction(torch.autograd.Function):
 
 
 class _SpConvFunctionBF16(torch.autograd.Function):
-    """Mixed-precision training form (config.compute == "bf16"): forward and dgrad run the tcgen05 gather-GEMM with
-    bf16 operands and fp32 accumulation — dgrad is the SAME kernel over the transposed rulebook with the transposed
-    weights, din[i] = sum_k dout[nbr_t[k][i]] @ W[:,k,:] — and wgrad stays on the fp32 kernel (fp32 features and
-    gradients).  Outputs and gradients are fp32 tensors."""
+    """Mixed-precision training form (config.compute == "bf16"): forward, dgrad and wgrad all run on the tcgen05
+    kernels with bf16 operands and fp32 accumulation.  dgrad is the forward gather-GEMM over the transposed rulebook
+    with the transposed weights, din[i] = sum_k dout[nbr_t[k][i]] @ W[:,k,:]; wgrad reduces over the output rows with
+    the gathered rows as MN-major operands (conv_wgrad.cu).  The bf16 image of the input is what is saved for the
+    backward pass.  Outputs and gradients are fp32 tensors.  config.wgrad = "f32" keeps wgrad on the fp32 check
+    kernel (fp32 features and gradients)."""
 
     @staticmethod
     def forward(ctx, feats, weight, bias, rb, gather_map, scatter_map_fn):
@@ -217,7 +220,8 @@ class _SpConvFunctionBF16(torch.autograd.Function):
         xb = ops.cast_pad(feats, ops.pad16(Cin))
         out = ops.spconv_fwd_bf16(xb, ops.pack_weight_bf16(w3), int(w3.shape[1]), Cout, gather_map,
                                   bias=bias.detach().float() if bias is not None else None, out_dtype=torch.float32)
-        ctx.save_for_backward(feats, weight)
+        ctx.wgrad_f32 = config.wgrad == "f32"
+        ctx.save_for_backward(feats if ctx.wgrad_f32 else xb, weight)
         ctx.gather_map, ctx.scatter_map_fn, ctx.has_bias = gather_map, scatter_map_fn, bias is not None
         return out
 
@@ -228,15 +232,19 @@ class _SpConvFunctionBF16(torch.autograd.Function):
         w3 = weight.detach().reshape(Cout, -1, Cin).contiguous().float()
         K = int(w3.shape[1])
         dout = dout.contiguous().float()
+        doutb = ops.cast_pad(dout, Cout)
         din = dw = db = None
         if ctx.needs_input_grad[0]:
             cin_p = ops.pad16(Cin)                       # the kernel's N must be 16 / 32 / 64 / 128: zero rows beyond Cin
             wt = torch.zeros((cin_p, K, Cout), dtype=torch.float32, device=w3.device)
             wt[:Cin] = w3.permute(2, 1, 0)
-            din = ops.spconv_fwd_bf16(ops.cast_pad(dout, Cout), ops.pack_weight_bf16(wt), K, cin_p, ctx.scatter_map_fn(),
+            din = ops.spconv_fwd_bf16(doutb, ops.pack_weight_bf16(wt), K, cin_p, ctx.scatter_map_fn(),
                                       out_dtype=torch.float32)[:, :Cin].contiguous()
         if ctx.needs_input_grad[1]:
-            dw = ops.spconv_wgrad_f32(feats, dout, ctx.gather_map).reshape(weight.shape)
+            if ctx.wgrad_f32:
+                dw = ops.spconv_wgrad_f32(feats, dout, ctx.gather_map).reshape(weight.shape)
+            else:
+                dw = ops.spconv_wgrad_bf16(feats, doutb, ctx.gather_map, Cin).reshape(weight.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dout.sum(0)
         return din, dw, db, None, None, None

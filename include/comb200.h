@@ -197,6 +197,17 @@ int comb_spconv_fwd_bf16(const void* in_feats, int Cin_p, const void* wpacked, i
                          int epi_flags, const float* bias, const float* scale, const float* shift,
                          const void* residual, void* out, int out_dtype, void* stream);
 
+/* wgrad on the tensor cores (a8): dW[co,k,ci] = sum_o dout[o,co] * in[nbr[k][o], ci] with bf16 operands and fp32
+ * accumulation in TMEM (tcgen05.mma, both operands MN-major: the gathered rows are used as they are gathered).
+ *  in_feats [ni, Cin_p] bf16 (zero padded beyond Cin), dout [no, Cout] bf16, dweight [Cout, K, Cin] fp32 (overwritten).
+ *  workspace: comb_spconv_wgrad_bf16_workspace_bytes(...) bytes of device memory (per-row-chunk partial sums that a
+ *  second kernel adds in a fixed order: the result is deterministic).  Supported: Cin_p, Cout in {16, 32, 64, 128}.
+ * Replaces the wgrad GEMMs of spconv's SparseConvolution backward (spconv_backbone.py:12-15,38-45,191-232). */
+size_t comb_spconv_wgrad_bf16_workspace_bytes(int Cin_p, int Cin, int Cout, int K, int no_max);
+int comb_spconv_wgrad_bf16(const void* in_feats, int Cin_p, int Cin, const void* dout, int Cout, int K,
+                           const int* nbr, int ld, int no_max, const int* no_dev, float* dweight,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* Debug hook: CTA 0 of every following comb_spconv_fwd_bf16 launch records clock64 stamps of its pipeline
  * events (first 512 chunks, 8 int64 slots each) into `buf` (device, 32 KB); NULL switches tracing off. */
 int comb_debug_conv_trace(void* buf);

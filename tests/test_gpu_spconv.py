@@ -131,6 +131,60 @@ def test_bf16_many_tiles_persistent_loop(C, n):
     assert rel_err(got, want) < 1e-4
 
 
+@pytest.mark.parametrize("Cin,Cout", [(5, 16), (16, 16), (16, 32), (32, 16), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128)])
+@pytest.mark.parametrize("subm", [True, False])
+def test_wgrad_bf16_tensor_core(Cin, Cout, subm):
+    """a8 wgrad on tcgen05 (MN-major operands, conv_wgrad.cu) vs the oracle: 1e-4 on the same bf16-rounded operands
+    (exact bf16 products, fp32 accumulation), 2e-2 against the un-rounded fp32 problem."""
+    coords, out_coords, nbr, feats, W, rng = make_case(Cin * 19 + Cout, 3000, Cin, Cout, st=(1, 1, 1) if subm else (2, 2, 2), subm=subm)
+    dout = rng.normal(size=(nbr.shape[1], Cout)).astype(np.float32)
+    want = oracle.conv_wgrad(bf16_round(feats), bf16_round(dout), nbr)
+    x = ops.cast_pad(cuda(feats), ops.pad16(Cin))
+    g = ops.cast_pad(cuda(dout), Cout)
+    got = ops.spconv_wgrad_bf16(x, g, cuda(nbr), Cin)
+    assert tuple(got.shape) == (Cout, 27, Cin)
+    got = got.cpu().numpy()
+    assert rel_err(got, want) < 1e-4
+    assert rel_err(got, oracle.conv_wgrad(feats, dout, nbr)) < TOL_BF16
+    # deterministic: fixed-order reduction over the row chunks, no atomics
+    assert np.array_equal(got, ops.spconv_wgrad_bf16(x, g, cuda(nbr), Cin).cpu().numpy())
+
+
+def test_wgrad_bf16_kernel_311_and_device_count():
+    """spconv_down2 shape (k=(3,1,1), stride (2,1,1), 128 -> 128) and a device-side row count below the bound."""
+    rng = np.random.default_rng(5)
+    shape = [12, 40, 40]
+    coords = clustered_coords(rng, 3000, 2, shape, clusters=10, spread=2.5)
+    ks, st, pd, dl = (3, 1, 1), (2, 1, 1), (0, 0, 0), (1, 1, 1)
+    oshape = oracle.conv_out_shape(shape, ks, st, pd, dl)
+    out_coords = oracle.conv_out_coords(coords, oshape, ks, st, pd, dl)
+    nbr = oracle.nbrmap(out_coords, coords, shape, ks, st, pd, dl)
+    no = nbr.shape[1]
+    feats = rng.normal(size=(len(coords), 128)).astype(np.float32)
+    dout = rng.normal(size=(no, 128)).astype(np.float32)
+    x, g = ops.cast_pad(cuda(feats), 128), ops.cast_pad(cuda(dout), 128)
+    got = ops.spconv_wgrad_bf16(x, g, cuda(nbr), 128).cpu().numpy()
+    assert rel_err(got, oracle.conv_wgrad(bf16_round(feats), bf16_round(dout), nbr)) < 1e-4
+    cut = no - 101
+    n_dev = torch.tensor([cut], dtype=torch.int32, device="cuda")
+    got = ops.spconv_wgrad_bf16(x, g, cuda(nbr), 128, no_dev=n_dev).cpu().numpy()
+    want = oracle.conv_wgrad(bf16_round(feats), bf16_round(dout)[:cut], np.ascontiguousarray(nbr[:, :cut]))
+    assert rel_err(got, want) < 1e-4
+
+
+@pytest.mark.parametrize("C,n", [(16, 50000), (32, 50000), (64, 60000), (128, 60000)])
+def test_wgrad_bf16_many_tiles(C, n):
+    """Every CTA walks several 64-row tiles: the stage ring wraps, accumulators stay in tensor memory across tiles."""
+    rng = np.random.default_rng(40 + C)
+    coords = random_coords(rng, n, 4, [16, 96, 96])
+    nbr = oracle.subm_nbrmap(coords, [16, 96, 96])
+    feats = rng.normal(size=(len(coords), C)).astype(np.float32)
+    dout = rng.normal(size=(len(coords), C)).astype(np.float32)
+    want = oracle.conv_wgrad(bf16_round(feats), bf16_round(dout), nbr)
+    got = ops.spconv_wgrad_bf16(ops.cast_pad(cuda(feats), C), ops.cast_pad(cuda(dout), C), cuda(nbr), C).cpu().numpy()
+    assert rel_err(got, want) < 1e-4
+
+
 def test_module_autograd_matches_oracle():
     """SubMConv3d / SparseConv3d modules (spconv API) incl. backward through torch autograd."""
     coords, out_coords, nbr, feats, W, rng = make_case(13, 1500, 16, 32, st=(2, 2, 2), subm=False)
@@ -194,8 +248,9 @@ print("alt-ok")
 @pytest.mark.parametrize("Cin,Cout,subm", [(5, 16, True), (16, 32, False), (64, 64, True), (128, 128, False)])
 def test_module_autograd_bf16_training_form(Cin, Cout, subm):
     """config.compute = "bf16" with autograd: forward and dgrad on the tcgen05 kernel (dgrad = the same gather-GEMM over
-    the transposed rulebook with W^T), wgrad on the fp32 kernel.  vs the oracle: 2e-2 for the bf16-operand results
-    (forward, dgrad), 1e-4 for wgrad and the bias gradient (fp32 arithmetic on fp32 operands)."""
+    the transposed rulebook with W^T), wgrad on the tcgen05 MN-major kernel.  vs the oracle: 2e-2 for the bf16-operand
+    results (forward, dgrad, wgrad), 1e-4 for the bias gradient (fp32 arithmetic on fp32 operands); with
+    config.wgrad = "f32" the weight gradient comes from the fp32 check kernel and meets 1e-4."""
     st = (1, 1, 1) if subm else (2, 2, 2)
     coords, out_coords, nbr, feats, W, rng = make_case(Cin * 3 + Cout, 2500, Cin, Cout, st=st, subm=subm)
     mod = (sparse.SubMConv3d(Cin, Cout, 3, bias=True, indice_key="k") if subm else
@@ -215,5 +270,14 @@ def test_module_autograd_bf16_training_form(Cin, Cout, subm):
     assert y.features.dtype == torch.float32 and x.grad.dtype == torch.float32
     assert rel_err(y.features.detach().cpu().numpy(), oracle.conv_fwd(feats, W, nbr, bias)) < TOL_BF16
     assert rel_err(x.grad.cpu().numpy(), oracle.conv_dgrad(dout, W, nbr, len(coords))) < TOL_BF16
-    assert rel_err(mod.weight.grad.reshape(Cout, 27, Cin).cpu().numpy(), oracle.conv_wgrad(feats, dout, nbr)) < TOL_F32
+    assert rel_err(mod.weight.grad.reshape(Cout, 27, Cin).cpu().numpy(), oracle.conv_wgrad(feats, dout, nbr)) < TOL_BF16
     assert rel_err(mod.bias.grad.cpu().numpy(), dout.sum(0)) < TOL_F32
+    old_w = sparse.config.wgrad
+    sparse.config.compute, sparse.config.wgrad = "bf16", "f32"
+    try:
+        mod.weight.grad = None
+        x2 = cuda(feats).requires_grad_(True)
+        mod(sparse.SparseConvTensor(x2, cuda(coords), [12, 40, 40], 2)).features.backward(cuda(dout))
+    finally:
+        sparse.config.compute, sparse.config.wgrad = old, old_w
+    assert rel_err(mod.weight.grad.reshape(Cout, 27, Cin).cpu().numpy(), oracle.conv_wgrad(feats, dout, nbr)) < TOL_F32
