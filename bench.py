@@ -346,12 +346,14 @@ def box_ops_leg(torch, frame, peaks):
 
 
 # ------------------------------------------------------------------------------------------- training leg (configs[2])
-def train_leg(torch, frames):
+def train_leg(torch, frames, world=1, local_rank=0):
     """BASELINE configs[2], the part of a training step that is on this path (row a8): VoxelResBackBone8x in TRAIN mode
-    (module path: fp32 sparse convs with autograd — dgrad through transposed rulebooks, wgrad — BatchNorm1d batch
-    statistics), forward + backward + SGD step on a batch of 2 frames.  fp32 check arithmetic on CUDA cores: a
-    correctness path, not yet a tensor-core one."""
-    from com_b200 import models, ops, synth
+    (module path with autograd, BatchNorm1d batch statistics), forward + backward + SGD step on a batch of 2 frames per
+    GPU.  Two arithmetic forms: the fp32 check kernels (CUDA cores) and the mixed-precision form where forward, dgrad
+    and wgrad all run on the tcgen05 kernels (bf16 operands, fp32 accumulation).  Under torchrun (world > 1) the
+    backbone is wrapped in torch DistributedDataParallel (NCCL gradient all-reduce over NVLink, as the reference's
+    tools/train.py:166 does); every rank steps on its own 2 frames, the reported time is the max over ranks."""
+    from com_b200 import dist as cdist, models, ops, sparse, synth
     dev = torch.device("cuda", torch.cuda.current_device())
     fr = frames[:2]
     offs = np.concatenate([[0], np.cumsum([len(f) for f in fr])]).astype(int).tolist()
@@ -359,40 +361,98 @@ def train_leg(torch, frames):
     torch.manual_seed(0)
     net = models.VoxelResBackBone8x(None, 5, synth.GRID_SIZE).to(dev).train()
     net.fused = False
+    model = net
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank])
     opt = torch.optim.SGD(net.parameters(), lr=1e-3)
+    vfe = models.MeanVFE(None, 5)
 
     def step():
         r = ops.voxelize(pts, offs, synth.VOXEL_SIZE, synth.POINT_CLOUD_RANGE, synth.MAX_POINTS_PER_VOXEL,
                          synth.MAX_NUMBER_OF_VOXELS)
         m = int(r["counts"][2])
-        bd = models.MeanVFE(None, 5)({"voxels": r["voxels"][:m], "voxel_num_points": r["num_points"][:m]})
-        bd = net({"batch_size": 2, "voxel_features": bd["voxel_features"], "voxel_coords": r["coords"][:m].float()})
+        bd = vfe({"voxels": r["voxels"][:m], "voxel_num_points": r["num_points"][:m]})
+        bd = model({"batch_size": 2, "voxel_features": bd["voxel_features"], "voxel_coords": r["coords"][:m].float()})
         loss = bd["encoded_spconv_tensor"].features.float().square().mean()
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
-        return float(loss.detach())
+        return loss.detach()
 
-    from com_b200 import sparse
     res = {"workload": "configs[2], sparse part: voxelize + VoxelResBackBone8x train-mode forward + backward + SGD step, "
-                       "batch 2 (module path with autograd)"}
-    old = sparse.config.compute
+                       "batch 2 per GPU (module path with autograd)%s" % (
+                           ", torch DDP over %d GPUs (NCCL gradient all-reduce)" % world if world > 1 else ""),
+           "n_gpus": world}
+    old = (sparse.config.compute, sparse.config.wgrad)
     try:
-        for mode, label in (("f32", "fp32_check"), ("bf16", "bf16_fwd_dgrad_tcgen05")):
-            sparse.config.compute = mode
+        for compute, wgrad, label, reps in (("f32", "f32", "fp32_check", 2),
+                                            ("bf16", "f32", "bf16_fwd_dgrad_tcgen05_wgrad_fp32", 2),
+                                            ("bf16", "bf16", "bf16_fwd_dgrad_wgrad_tcgen05", 10)):
+            sparse.config.compute, sparse.config.wgrad = compute, wgrad
             step()
+            step()
+            cdist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            reps = 3
             for _ in range(reps):
                 last = step()
             e1.record()
             torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / reps
-            res[label] = {"ms_per_step": ms, "frames_per_s": 2e3 / ms, "loss_finite": bool(np.isfinite(last))}
+            ms = cdist.max_over_ranks(e0.elapsed_time(e1) / reps)
+            res[label] = {"ms_per_step": ms, "frames_per_s": 2e3 * world / ms,
+                          "loss_finite": bool(np.isfinite(float(last)))}
+        # the tcgen05 wgrad launches of one step, replayed back to back behind a spin kernel (launches queued, no host
+        # gaps) with CUDA events around each: per-layer device time and algorithmic TFLOP/s (2 * pairs * Cin * Cout)
+        class _Capture:
+            def __init__(self):
+                self.calls = []
+
+            def begin(self, tag, **info):
+                if tag == "spconv_wgrad_bf16":
+                    self.calls.append(info)
+
+            def end(self):
+                pass
+
+        cap = _Capture()
+        sparse.config.compute, sparse.config.wgrad = "bf16", "bf16"
+        ops.set_profiler(cap)
+        try:
+            step()
+        finally:
+            ops.set_profiler(None)
+        torch.cuda.synchronize()
+        evs = []
+        torch.cuda._sleep(int(6e6))
+        for c in cap.calls:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.spconv_wgrad_bf16(c["feats"], c["dout"], c["nbr"], c["cin_real"])
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        layers, tot_ms, tot_fl = {}, 0.0, 0.0
+        for c, (e0, e1) in zip(cap.calls, evs):
+            ms = e0.elapsed_time(e1)
+            fl = 2.0 * float((c["nbr"] >= 0).sum().item()) * c["cin"] * c["cout"]
+            key = "%dx%d_K%d" % (c["cin"], c["cout"], c["K"])
+            a = layers.setdefault(key, {"n": 0, "ms": 0.0, "flops": 0.0})
+            a["n"] += 1
+            a["ms"] += ms
+            a["flops"] += fl
+            tot_ms += ms
+            tot_fl += fl
+        if tot_ms > 0:
+            peaks = load_peaks()
+            res["wgrad_tcgen05"] = {
+                "kernel": "spconv_wgrad_tc_kernel (MN-major operands, accumulators in tensor memory) + wgrad_reduce_kernel",
+                "launches_per_step": len(cap.calls), "ms_per_step": tot_ms, "achieved": tot_fl / tot_ms / 1e9,
+                "unit": "TFLOP/s", "peak": peaks["tf_sust"], "frac": tot_fl / tot_ms / 1e9 / peaks["tf_sust"],
+                "layers": {k: {"ms_per_launch": v["ms"] / v["n"], "tflops": v["flops"] / v["ms"] / 1e9}
+                           for k, v in layers.items()}}
     finally:
-        sparse.config.compute = old
+        sparse.config.compute, sparse.config.wgrad = old
     return res
 
 
@@ -600,6 +660,13 @@ def ours(args):
     t_e2e_max = cdist.max_over_ranks(t_e2e)
     total_frames = world * BATCH * args.steps
 
+    train = None
+    if not args.no_cpu:                  # secondary leg, every rank takes part (DDP all-reduce when world > 1)
+        try:
+            train = train_leg(torch, frames, world, local_rank)
+        except Exception as e:           # the secondary leg must never take the headline line down
+            train = {"error": "%s: %s" % (type(e).__name__, e)}
+
     line = None
     if rank == 0:
         conv = fam.get("spconv_fwd_bf16", dict(ms=1e-9, flops=0, bytes=0, launches=1))
@@ -670,10 +737,8 @@ def ours(args):
                 line["box_ops"] = box_ops_leg(torch, frames[0], peaks)
             except Exception as e:       # the secondary leg must never take the headline line down
                 line["box_ops"] = {"error": "%s: %s" % (type(e).__name__, e)}
-            try:
-                line["train_sparse_part"] = train_leg(torch, frames)
-            except Exception as e:
-                line["train_sparse_part"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        if train is not None:
+            line["train_sparse_part"] = train
         print(json.dumps(line))
     cdist.barrier()
     return line
@@ -685,7 +750,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline, box_ops and train legs")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="launch kernels one by one (no CUDA graph)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -123,20 +123,42 @@ __global__ void __launch_bounds__(kWgThreads, 1) spconv_wgrad_tc_kernel(WgParams
     const int nA = ntap << LOG_RP;                   // 16-byte pieces of the A blocks of one stage
     const int log_ppb = Cout == 16 ? 1 : (Cout == 32 ? 2 : (Cout == 64 ? 3 : 4));
     const int nB = kR << log_ppb;
+    // One global-memory latency per stage on the critical path instead of three: the neighbour indices of a tile's
+    // first batch of pieces are loaded one tile ahead (idx_next), the dout pieces are loaded together with the
+    // gathered rows, and the wait for the stage to be free comes after the loads have been issued.
+    auto load_idx = [&](int r0, int e0, int (&idx)[kWgUnroll]) {
+#pragma unroll
+      for (int u = 0; u < kWgUnroll; ++u) {
+        const int e = e0 + u * kWgProducers;
+        const int t = e >> LOG_RP, row = (e >> LOG_PPO) & (kR - 1);
+        idx[u] = -1;
+        if (e < nA && r0 + row < no) idx[u] = __ldg(p.nbr + (size_t)(k0 + t) * p.ld + r0 + row);
+      }
+    };
+    int idx_next[kWgUnroll];
+    load_idx(tile0 * kR, tid, idx_next);
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < my_tiles; ++it) {
       const int r0 = (tile0 + it) * kR;
-      mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
       const uint32_t stage = smem_base + (uint32_t)s * stage_bytes;
+      uint4 vb[2];                                   // nB <= 1024 pieces: at most two per thread
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int e = tid + u * kWgProducers;
+        const int row = e >> log_ppb, pc = e & ((1 << log_ppb) - 1);
+        vb[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (e < nB && r0 + row < no)
+          vb[u] = __ldg(reinterpret_cast<const uint4*>(dout_b + (size_t)(r0 + row) * (Cout * 2) + pc * 16));
+      }
+      bool waited = false;
       for (int e0 = tid; e0 < nA; e0 += kWgProducers * kWgUnroll) {
         int idx[kWgUnroll];
+        if (e0 == tid) {
 #pragma unroll
-        for (int u = 0; u < kWgUnroll; ++u) {
-          const int e = e0 + u * kWgProducers;
-          const int t = e >> LOG_RP, row = (e >> LOG_PPO) & (kR - 1);
-          idx[u] = -1;
-          if (e < nA && r0 + row < no) idx[u] = __ldg(p.nbr + (size_t)(k0 + t) * p.ld + r0 + row);
+          for (int u = 0; u < kWgUnroll; ++u) idx[u] = idx_next[u];
+        } else {
+          load_idx(r0, e0, idx);
         }
         uint4 v[kWgUnroll];
 #pragma unroll
@@ -144,6 +166,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) spconv_wgrad_tc_kernel(WgParams
           const int pc = (e0 + u * kWgProducers) & (PPO - 1);
           v[u] = make_uint4(0u, 0u, 0u, 0u);
           if (idx[u] >= 0) v[u] = __ldg(reinterpret_cast<const uint4*>(in_b + (size_t)(uint32_t)idx[u] * (CIN * 2) + pc * 16));
+        }
+        if (e0 == tid && it + 1 < my_tiles) load_idx(r0 + kR, tid, idx_next);
+        if (!waited) {
+          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+          waited = true;
         }
 #pragma unroll
         for (int u = 0; u < kWgUnroll; ++u) {
@@ -165,13 +192,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) spconv_wgrad_tc_kernel(WgParams
           }
         }
       }
-      for (int e = tid; e < nB; e += kWgProducers) {
-        const int row = e >> log_ppb, pc = e & ((1 << log_ppb) - 1);
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r0 + row < no) v = __ldg(reinterpret_cast<const uint4*>(dout_b + (size_t)(r0 + row) * (Cout * 2) + pc * 16));
-        const uint32_t dst = stage + b_off + (uint32_t)(pc >> 3) * kCbBytes + swz_off(row, pc & 7);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                     : "memory");
+      if (!waited) mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int e = tid + u * kWgProducers;
+        if (e < nB) {
+          const int row = e >> log_ppb, pc = e & ((1 << log_ppb) - 1);
+          const uint32_t dst = stage + b_off + (uint32_t)(pc >> 3) * kCbBytes + swz_off(row, pc & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(vb[u].x), "r"(vb[u].y), "r"(vb[u].z),
+                       "r"(vb[u].w)
+                       : "memory");
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));   // release: the warp's stores happen-before the MMA warp's wait
@@ -248,14 +279,29 @@ __global__ void __launch_bounds__(kWgThreads, 1) spconv_wgrad_tc_kernel(WgParams
   }
 }
 
-// dW[e] = sum over row chunks of partial[c][e], in chunk order
+// dW[e] = sum over the row chunks of partial[c][e] in a FIXED order (deterministic): a block owns 64 elements, its
+// four thread rows sum the chunks c = j, j+4, j+8, ... (independent loads, four in flight) and the four slice sums
+// are combined as (s0 + s1) + (s2 + s3).
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int nchunks, int n,
                                                             float* __restrict__ dw) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  __shared__ float sm[4][64];
+  const int i = blockIdx.x * 64 + (threadIdx.x & 63), j = threadIdx.x >> 6;
   float s = 0.0f;
-  for (int c = 0; c < nchunks; ++c) s += __ldg(partial + (size_t)c * n + i);
-  dw[i] = s;
+  if (i < n) {
+    int c = j;
+    for (; c + 12 < nchunks; c += 16) {
+      const float a0 = __ldg(partial + (size_t)c * n + i), a1 = __ldg(partial + (size_t)(c + 4) * n + i);
+      const float a2 = __ldg(partial + (size_t)(c + 8) * n + i), a3 = __ldg(partial + (size_t)(c + 12) * n + i);
+      s += a0;
+      s += a1;
+      s += a2;
+      s += a3;
+    }
+    for (; c < nchunks; c += 4) s += __ldg(partial + (size_t)c * n + i);
+  }
+  sm[j][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (j == 0 && i < n) dw[i] = (sm[0][threadIdx.x] + sm[1][threadIdx.x]) + (sm[2][threadIdx.x] + sm[3][threadIdx.x]);
 }
 
 struct WgPlan {
@@ -365,7 +411,7 @@ extern "C" int comb_spconv_wgrad_bf16(const void* in_feats, int Cin_p, int Cin, 
     default: rc = dispatch_nb<128>(p, pl, stream); break;
   }
   if (rc != COMB_OK) return rc;
-  wgrad_reduce_kernel<<<cdiv((long long)n, 256), 256, 0, stream>>>(p.partial, pl.nchunks, (int)n, dweight);
+  wgrad_reduce_kernel<<<cdiv((long long)n, 64), 256, 0, stream>>>(p.partial, pl.nchunks, (int)n, dweight);
   COMB_LAUNCH_CHECK();
   return COMB_OK;
 }

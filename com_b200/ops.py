@@ -375,7 +375,8 @@ def spconv_wgrad_bf16(feats, dout, nbr, Cin, no_dev=None):
         raise RuntimeError("unsupported conv shape for the bf16 wgrad: Cin_p=%d Cin=%d Cout=%d K=%d" % (cin_p, Cin, Cout, K))
     ws = _ws(nbytes, feats.device)
     dw = torch.empty((Cout, K, Cin), dtype=torch.float32, device=feats.device)
-    with _Scope("spconv_wgrad_bf16", cin=cin_p, cout=Cout, K=K, nbr=nbr, no=no, no_dev=no_dev, ni=int(feats.shape[0])):
+    with _Scope("spconv_wgrad_bf16", cin=cin_p, cout=Cout, K=K, nbr=nbr, no=no, no_dev=no_dev, ni=int(feats.shape[0]),
+                feats=feats, dout=dout, cin_real=Cin):
         check(lib.comb_spconv_wgrad_bf16(_p(feats), cin_p, Cin, _p(dout), Cout, K, _p(nbr), ld, no, _p(no_dev), _p(dw),
                                          _p(ws), nbytes, _stream()), "comb_spconv_wgrad_bf16")
     return dw
