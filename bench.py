@@ -456,6 +456,54 @@ def train_leg(torch, frames, world=1, local_rank=0):
     return res
 
 
+def multisweep_leg(torch, rank=0):
+    """BASELINE configs[4] per GPU: ONE 3-sweep aggregated frame (~500k points x 6 features incl. the timestamp, voxel
+    cap 180 000 of waymo_dataset_multiframe.yaml:83-89) through voxelize + MeanVFE + VoxelResBackBone8x(6 input
+    channels) + HeightCompression as one CUDA-graph replay, followed by the rotated NMS of 500 score-sorted boxes
+    (CenterHead post-processing, model_nms_utils.py:6-25) on the same stream.  Device time over 20 steps behind a
+    parked stream; at N GPUs every rank takes its own frame (batch 8 over 8 B200 = 1 frame per GPU)."""
+    from com_b200 import ops, pipeline, synth
+    dev = torch.device("cuda", torch.cuda.current_device())
+    seed = 3000 + rank
+    f = os.path.join("/tmp", "comb200_frames", "frame3_%d.npy" % seed)
+    if os.path.exists(f):
+        fr = np.load(f)
+    else:
+        fr = synth.make_frame(seed=seed, sweeps=3)
+        try:
+            np.save(f, fr)
+        except OSError:
+            pass
+    pipe = pipeline.FramePipeline(input_channels=6, max_voxels=180000, device=dev, seed=0, use_graph=True)
+    pts, offs = torch.from_numpy(fr).to(dev), [0, int(fr.shape[0])]
+    cl_np = synth.make_clustered_boxes(500, seed=21)
+    cl = torch.from_numpy(cl_np).to(dev)
+    trig4 = torch.from_numpy(ops.box_trig4_host(cl_np)).to(dev)
+
+    def step():
+        h = pipe.enqueue_device(pts, offs)
+        ops.nms(cl, 0.7, rotated=True, flavour="gpu", trig=trig4)
+        return h
+
+    for _ in range(3):
+        h = step()
+    out = pipe.finish(h)
+    torch.cuda.synchronize()
+    torch.cuda._sleep(10_000_000)
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"workload": "configs[4] per GPU: one 3-sweep frame (%d points x 6), voxel cap 180000: voxelize+MeanVFE+"
+                        "VoxelResBackBone8x+HeightCompression (one CUDA graph) + rotated NMS of 500 boxes" % fr.shape[0],
+            "voxels": int(out["voxel_coords"].shape[0]), "encoded_rows": int(out["encoded_spconv_tensor"].features.shape[0]),
+            "ms_per_frame": ms, "frames_per_s_per_gpu": 1e3 / ms}
+
+
 # ------------------------------------------------------------------------------------------- GPU arm
 def ours(args):
     import torch
@@ -739,6 +787,11 @@ def ours(args):
                 line["box_ops"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if train is not None:
             line["train_sparse_part"] = train
+        if not args.no_cpu:
+            try:
+                line["multisweep_part"] = multisweep_leg(torch, rank)
+            except Exception as e:
+                line["multisweep_part"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line))
     cdist.barrier()
     return line
