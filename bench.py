@@ -267,7 +267,7 @@ def reference_arm(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), flush=True)
 
 
 # ------------------------------------------------------------------------------------------- box ops (configs[0])
@@ -792,7 +792,7 @@ def ours(args):
                 line["multisweep_part"] = multisweep_leg(torch, rank)
             except Exception as e:
                 line["multisweep_part"] = {"error": "%s: %s" % (type(e).__name__, e)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     cdist.barrier()
     return line
 
@@ -806,6 +806,12 @@ def main():
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline, box_ops and train legs")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="launch kernels one by one (no CUDA graph)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: native libraries that write to file descriptor 1 (NCCL prints its version
+    # banner there when DDP creates its communicator) are sent to stderr; python's own stdout keeps the real one
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         reference_arm(args)
     else:
