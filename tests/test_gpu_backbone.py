@@ -317,3 +317,57 @@ def test_multisweep_six_channel_pipeline():
         assert g.spatial_shape == w.spatial_shape and np.array_equal(g.indices.cpu().numpy(), wc[o])
         assert rel_err(g.features.float().cpu().numpy(), wf[o].astype(np.float64)) < 2e-2
     assert got[-1].features.shape[0] > 100
+
+
+_FRAMES = {}
+
+
+def _waymo_frame(seed):
+    if seed not in _FRAMES:
+        _FRAMES[seed] = synth.make_frame(seed=seed)
+    return _FRAMES[seed]
+
+
+@pytest.mark.parametrize("level,Cin,Cout,subm", [(0, 16, 16, True), (0, 16, 32, False), (1, 32, 32, True),
+                                                  (2, 64, 64, True), (3, 128, 128, True)])
+def test_full_size_adjoint_identities_bf16_training_form(level, Cin, Cout, subm):
+    """Size-independent parity property of the backward (a8) at BASELINE scale: the convolution is bilinear in
+    (features, weights), so the three tcgen05 kernels — forward gather-GEMM, dgrad (the same kernel over the transposed
+    rulebook with W^T) and wgrad (MN-major operands, accumulators resident in tensor memory) — must give the SAME
+    number for <conv(x; W), g> = <x, dgrad(g; W)> = <W, wgrad(x, g)> on a Waymo-shaped frame (~80 k voxels at level 0,
+    coarsened by 2 per level).  Operands are bf16-representable, accumulation is fp32: 1e-3 relative."""
+    frame = _waymo_frame(1234)
+    pts = torch.from_numpy(frame).cuda()
+    r = ops.voxelize(pts, [0, len(frame)], synth.VOXEL_SIZE, synth.POINT_CLOUD_RANGE, 5, 150000)
+    m = int(r["counts"][1])
+    coords = r["coords"][:m].clone()
+    shape = [41, 1504, 1504]
+    for _ in range(level):                       # coarsen like the strided levels of the backbone
+        coords[:, 1:] = coords[:, 1:] // 2
+        shape = [(s + 1) // 2 for s in shape]
+        key = ((coords[:, 0].long() * shape[0] + coords[:, 1]) * shape[1] + coords[:, 2]) * shape[2] + coords[:, 3]
+        first = np.unique(key.cpu().numpy(), return_index=True)[1]          # one row per coarse cell
+        coords = coords[torch.from_numpy(np.sort(first)).cuda()].contiguous()
+    n = int(coords.shape[0])
+    assert n > 2000
+    from com_b200 import sparse
+    mod = (sparse.SubMConv3d(Cin, Cout, 3, bias=False, indice_key="k") if subm else
+           sparse.SparseConv3d(Cin, Cout, 3, stride=2, padding=1, bias=False, indice_key="k")).cuda()
+    g = torch.Generator(device="cuda").manual_seed(level * 7 + Cin)
+    with torch.no_grad():
+        mod.weight.copy_(torch.randn(mod.weight.shape, generator=g, device="cuda").bfloat16().float() / (27 * Cin) ** 0.5)
+        mod.weight.copy_(mod.weight.bfloat16().float())
+    x = torch.randn((n, Cin), generator=g, device="cuda").bfloat16().float().requires_grad_(True)
+    old = (sparse.config.compute, sparse.config.wgrad)
+    sparse.config.compute, sparse.config.wgrad = "bf16", "bf16"
+    try:
+        y = mod(SparseConvTensor(x, coords.int(), shape, 1)).features
+        gy = torch.randn(tuple(y.shape), generator=g, device="cuda").bfloat16().float()
+        y.backward(gy)
+    finally:
+        sparse.config.compute, sparse.config.wgrad = old
+    a = float((y.detach().double() * gy.double()).sum())
+    b = float((x.detach().double() * x.grad.double()).sum())
+    c = float((mod.weight.detach().double() * mod.weight.grad.double()).sum())
+    scale = float(y.detach().double().norm() * gy.double().norm())
+    assert abs(a - b) < 1e-3 * scale and abs(a - c) < 1e-3 * scale, (a, b, c, scale)
