@@ -36,6 +36,13 @@ def test_library_calls_without_gpu():
     assert lib.comb_spconv_packed_bytes(128, 27, 128) == 54 * 128 * 128
     assert lib.comb_spconv_packed_bytes(24, 27, 16) == 0
     assert lib.comb_voxelize_workspace_bytes(180000, 1, 150000, 5) > 0
+    # wgrad workspace = (row chunks) x (Cout*K*Cin) fp32 partials; one chunk per SM (148) when a CTA holds all 27 offsets
+    assert lib.comb_spconv_wgrad_bf16_workspace_bytes(16, 16, 16, 27, 160000) == 148 * 16 * 27 * 16 * 4
+    assert lib.comb_spconv_wgrad_bf16_workspace_bytes(16, 5, 16, 27, 160000) == 148 * 16 * 27 * 5 * 4
+    tiles = -(-15000 // 64)                      # 7 offset groups at 128 channels: 148 // 7 chunks of whole 64-row tiles
+    chunks = -(-tiles // -(-tiles // (148 // 7)))
+    assert lib.comb_spconv_wgrad_bf16_workspace_bytes(128, 128, 128, 27, 15000) == chunks * 128 * 27 * 128 * 4
+    assert lib.comb_spconv_wgrad_bf16_workspace_bytes(24, 24, 16, 27, 100) == 0      # unsupported channel count
 
 
 def test_argument_errors_are_status_codes():
