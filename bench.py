@@ -345,6 +345,87 @@ def box_ops_leg(torch, frame, peaks):
     return out
 
 
+# ------------------------------------------------------------------------------------------- COMAug leg (configs[3])
+def comaug_leg(torch, frame, peaks):
+    """BASELINE configs[3] (COMAug GT-database sampling, database_sampler_v2.py:564-631): rotated BEV IoU of 10 000
+    candidate boxes against 100 existing boxes and against each other (1e8 pairs, 400 MB of output: the one place where
+    the IoU kernel is HBM-class), then points_in_boxes removal of 35 boxes on the 180k-point frame.  Device time with
+    the launches queued; beside it the reference's own C++ on one host core, on a bounded sample (10k x 100 in full,
+    1000 x 1000 of the 10k x 10k, the 35-box removal in full)."""
+    import oracle
+    from com_b200 import ops, synth
+    from oracle import build_ref
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cand_np = np.concatenate([synth.make_clustered_boxes(9000, seed=61, centers=400),
+                              synth.make_boxes(1000, seed=64)]).astype(np.float32)
+    exist_np = synth.make_clustered_boxes(100, seed=62, centers=400)
+    rm_np = synth.make_boxes(35, seed=65)
+    rm_np[:, 2] = -1.0
+    pts_np = np.ascontiguousarray(frame[:, :3])
+    cand, exist, rm, pts = [torch.from_numpy(a).to(dev) for a in (cand_np, exist_np, rm_np, pts_np)]
+    tc, te = [torch.from_numpy(ops.box_trig4_host(a)).to(dev) for a in (cand_np, exist_np)]
+    trm = torch.from_numpy(ops.box_trig_host(rm_np)).to(dev)
+    o_small = torch.empty((10000, 100), dtype=torch.float32, device=dev)
+    o_full = torch.empty((10000, 10000), dtype=torch.float32, device=dev)
+    mask = torch.empty((35, int(pts.shape[0])), dtype=torch.int32, device=dev)
+
+    def timed(fn, reps=10):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        torch.cuda._sleep(10_000_000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms_small = timed(lambda: ops.boxes_bev(cand, exist, flavour="cpu", what="iou", trig_a=tc, trig_b=te, out=o_small))
+    ms_full = timed(lambda: ops.boxes_bev(cand, cand, flavour="cpu", what="iou", trig_a=tc, trig_b=tc, out=o_full))
+    ms_rm = timed(lambda: ops.points_in_boxes_mask(pts, rm, trm, out=mask))
+    by_full = 2 * 10000 * 28.0 + 1e8 * 4.0
+    out = {"workload": "configs[3]: rotated BEV IoU 10000 x 100 and 10000 x 10000 (400 MB out), points_in_boxes of 35 boxes "
+                       "on %d points" % pts.shape[0],
+           "iou_10k_x_100_ms": ms_small, "iou_10k_x_10k_ms": ms_full,
+           "iou_10k_x_10k": {"achieved_gbs": by_full / ms_full / 1e6, "frac_of_hbm_peak": by_full / ms_full / 1e6 / peaks["hbm"],
+                             "pairs_overlapping": int((o_full > 0).sum().item()), "bound": "hbm (IoU matrix write)"},
+           "points_in_boxes_35_ms": ms_rm}
+    kind = "port"
+    try:
+        if build_ref.available():
+            roi, i3d = build_ref.load_ref("ref_roiaware_pool3d_cuda"), build_ref.load_ref("ref_iou3d_nms_cuda")
+            kind = "reference"
+    except Exception:
+        kind = "port"
+    t0 = time.perf_counter()
+    if kind == "reference":
+        o = torch.zeros((10000, 100), dtype=torch.float32)
+        i3d.boxes_iou_bev_cpu(torch.from_numpy(cand_np), torch.from_numpy(exist_np), o)
+    else:
+        oracle.boxes_bev_cpu(cand_np, exist_np)
+    t1 = time.perf_counter()
+    sub = np.ascontiguousarray(cand_np[:1000])
+    if kind == "reference":
+        o = torch.zeros((1000, 1000), dtype=torch.float32)
+        i3d.boxes_iou_bev_cpu(torch.from_numpy(sub), torch.from_numpy(sub), o)
+    else:
+        oracle.boxes_bev_cpu(sub, sub)
+    t2 = time.perf_counter()
+    if kind == "reference":
+        o = torch.zeros((35, pts_np.shape[0]), dtype=torch.int32)
+        roi.points_in_boxes_cpu(torch.from_numpy(rm_np), torch.from_numpy(pts_np), o)
+    else:
+        oracle.points_in_boxes_cpu(pts_np, rm_np)
+    t3 = time.perf_counter()
+    out["cpu"] = {"kind": kind, "cores": 1, "iou_10k_x_100_ms": 1e3 * (t1 - t0),
+                  "iou_1000_x_1000_ms": 1e3 * (t2 - t1), "iou_10k_x_10k_ms_extrapolated": 1e3 * (t2 - t1) * 100.0,
+                  "points_in_boxes_35_ms": 1e3 * (t3 - t2),
+                  "sample": "10k x 100 and the 35-box removal in full; 1000 x 1000 of the 10k x 10k (x100 extrapolated)"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------- training leg (configs[2])
 def train_leg(torch, frames, world=1, local_rank=0):
     """BASELINE configs[2], the part of a training step that is on this path (row a8): VoxelResBackBone8x in TRAIN mode
@@ -785,6 +866,10 @@ def ours(args):
                 line["box_ops"] = box_ops_leg(torch, frames[0], peaks)
             except Exception as e:       # the secondary leg must never take the headline line down
                 line["box_ops"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            try:
+                line["comaug_part"] = comaug_leg(torch, frames[0], peaks)
+            except Exception as e:
+                line["comaug_part"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if train is not None:
             line["train_sparse_part"] = train
         if not args.no_cpu:

@@ -183,29 +183,80 @@ __device__ __forceinline__ float iou_from_overlap(const BoxRec& a, const BoxRec&
 }
 
 // ---------------------------------------------------------------- pairwise matrix
-constexpr int kTA = 8, kTB = 32;
+// A block owns a 16 x 128 tile of the (Na, Nb) matrix (2048 pairs, 256 threads).  Two phases:
+//   A. every thread runs the exact far-apart test on 8 consecutive columns of one row, writes the zeros of the tile
+//      with 16-byte stores and appends the pairs that may overlap to a queue in shared memory;
+//   B. the block walks the queue with all lanes busy: the expensive geometry (16 segment crossings, 8 corner tests,
+//      angular sort, shoelace: ~3000 instructions with local-memory arrays) runs only for those pairs.
+// (r1: one thread per pair left every warp with a single near pair — 12 % of the warps of the COMAug 10k x 10k case,
+// where 0.4 % of the pairs overlap — executing the slow path for one lane: 1.55 ms for 400 MB of output.)
+// Tile height TA: 16 rows for small matrices (more blocks than SMs at 500 x 500), 64 rows for large ones — a block
+// pays the latency of one slow-path round however few pairs are queued, so it should own as many pairs as possible.
+constexpr int kTB = 128, kPairsPerThread = 8;
 
-template <bool CPUF>
-__global__ void __launch_bounds__(kTA* kTB) boxes_bev_kernel(const float* __restrict__ boxes_a,
-                                                              const float* __restrict__ trig_a, int na,
-                                                              const float* __restrict__ boxes_b,
-                                                              const float* __restrict__ trig_b, int nb, int what,
-                                                              float* __restrict__ out) {
+template <bool CPUF, int kTA>
+__global__ void __launch_bounds__(256) boxes_bev_kernel(const float* __restrict__ boxes_a,
+                                                         const float* __restrict__ trig_a, int na,
+                                                         const float* __restrict__ boxes_b,
+                                                         const float* __restrict__ trig_b, int nb, int what,
+                                                         float* __restrict__ out, int vec_ok) {
   __shared__ BoxRec sa[kTA], sb[kTB];
-  const int tid = threadIdx.y * kTB + threadIdx.x;
+  __shared__ unsigned short queue[kTA * kTB];
+  __shared__ int qn;
+  const int tid = threadIdx.x;
   const int a0 = blockIdx.y * kTA, b0 = blockIdx.x * kTB;
-  if (tid < kTA) {
-    int i = a0 + tid;
-    if (i < na) make_box<CPUF>(boxes_a + (size_t)i * 7, CPUF ? trig_a + (size_t)i * 4 : nullptr, sa[tid]);
-  } else if (tid >= 32 && tid < 32 + kTB) {
-    int j = b0 + tid - 32;
-    if (j < nb) make_box<CPUF>(boxes_b + (size_t)j * 7, CPUF ? trig_b + (size_t)j * 4 : nullptr, sb[tid - 32]);
+  if (tid == 0) qn = 0;
+  static_assert(kTA <= 128 && kTA * kTB <= 65536, "tile must fit the 16-bit queue entries");
+  if (tid < kTB) {
+    const int j = b0 + tid;
+    if (j < nb) make_box<CPUF>(boxes_b + (size_t)j * 7, CPUF ? trig_b + (size_t)j * 4 : nullptr, sb[tid]);
+  } else if (tid < kTB + kTA) {
+    const int i = a0 + tid - kTB;
+    if (i < na) make_box<CPUF>(boxes_a + (size_t)i * 7, CPUF ? trig_a + (size_t)i * 4 : nullptr, sa[tid - kTB]);
   }
   __syncthreads();
-  const int i = a0 + threadIdx.y, j = b0 + threadIdx.x;
-  if (i >= na || j >= nb) return;
-  const float ov = overlap_area<CPUF>(sa[threadIdx.y], sb[threadIdx.x]);
-  out[(size_t)i * nb + j] = what ? ov : iou_from_overlap<CPUF>(sa[threadIdx.y], sb[threadIdx.x], ov);
+  // ---- phase A: far-apart test + zeros
+  const int c0 = (tid & 15) * kPairsPerThread;
+#pragma unroll 1
+  for (int r = tid >> 4; r < kTA; r += 16) {
+    const int i = a0 + r;
+    if (i < na && b0 + c0 < nb) {
+      const float ax = sa[r].cx, ay = sa[r].cy, arad = sa[r].rad;
+      unsigned near = 0;
+#pragma unroll
+      for (int u = 0; u < kPairsPerThread; ++u) {
+        if (b0 + c0 + u < nb) {
+          // the same exact early-out as overlap_area: further apart than the sum of the conservative radii => area +0
+          const float ddx = ax - sb[c0 + u].cx, ddy = ay - sb[c0 + u].cy, rr = arad + sb[c0 + u].rad;
+          if (!(ddx * ddx + ddy * ddy > rr * rr)) near |= 1u << u;
+        }
+      }
+      float* o = out + (size_t)i * nb + b0 + c0;
+      if (vec_ok && b0 + c0 + kPairsPerThread <= nb) {
+        reinterpret_cast<float4*>(o)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<float4*>(o)[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int u = 0; u < kPairsPerThread; ++u)
+          if (b0 + c0 + u < nb) o[u] = 0.0f;
+      }
+      if (near) {
+        const int base = atomicAdd(&qn, __popc(near));
+        int k = 0;
+#pragma unroll
+        for (int u = 0; u < kPairsPerThread; ++u)
+          if (near & (1u << u)) queue[base + k++] = (unsigned short)(r * kTB + c0 + u);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase B: the pairs that may overlap (the order of the queue does not matter: one writer per element)
+  const int n = qn;
+  for (int q = tid; q < n; q += 256) {
+    const int e = queue[q], rr = e / kTB, cc = e % kTB;
+    const float ov = overlap_area<CPUF>(sa[rr], sb[cc]);
+    out[(size_t)(a0 + rr) * nb + b0 + cc] = what ? ov : iou_from_overlap<CPUF>(sa[rr], sb[cc], ov);
+  }
 }
 
 // ---------------------------------------------------------------- NMS
@@ -487,12 +538,19 @@ extern "C" int comb_boxes_bev(const float* boxes_a, const float* trig_a, int na,
   if (na == 0 || nb == 0) return COMB_OK;
   COMB_CHECK_ARG(boxes_a && boxes_b && out, "comb_boxes_bev: null pointer");
   COMB_CHECK_ARG(flavour == 1 || (trig_a && trig_b), "comb_boxes_bev: cpu flavour needs host-libm trig tables");
-  dim3 grid(cdiv(nb, kTB), cdiv(na, kTA)), block(kTB, kTA);
+  const int vec_ok = (nb % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const bool big = (long long)na * nb >= (4ll << 20);        // enough 64-row tiles to fill the GPU several times
+  const int ta = big ? 64 : 16;
+  dim3 grid(cdiv(nb, kTB), cdiv(na, ta));
   COMB_CHECK_ARG(grid.y <= 65535, "comb_boxes_bev: too many rows (%d)", na);
-  if (flavour == 0)
-    boxes_bev_kernel<true><<<grid, block, 0, stream>>>(boxes_a, trig_a, na, boxes_b, trig_b, nb, what, out);
+  if (flavour == 0 && big)
+    boxes_bev_kernel<true, 64><<<grid, 256, 0, stream>>>(boxes_a, trig_a, na, boxes_b, trig_b, nb, what, out, vec_ok);
+  else if (flavour == 0)
+    boxes_bev_kernel<true, 16><<<grid, 256, 0, stream>>>(boxes_a, trig_a, na, boxes_b, trig_b, nb, what, out, vec_ok);
+  else if (big)
+    boxes_bev_kernel<false, 64><<<grid, 256, 0, stream>>>(boxes_a, trig_a, na, boxes_b, trig_b, nb, what, out, vec_ok);
   else
-    boxes_bev_kernel<false><<<grid, block, 0, stream>>>(boxes_a, trig_a, na, boxes_b, trig_b, nb, what, out);
+    boxes_bev_kernel<false, 16><<<grid, 256, 0, stream>>>(boxes_a, trig_a, na, boxes_b, trig_b, nb, what, out, vec_ok);
   COMB_LAUNCH_CHECK();
   return COMB_OK;
 }
