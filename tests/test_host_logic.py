@@ -85,3 +85,25 @@ def test_synthetic_frame_is_seeded_and_waymo_shaped():
     m = synth.make_frame(seed=5, sweeps=3, beams=4, n_az=200, side_rays=50)
     assert m.shape[1] == 6 and sorted(float(v) for v in np.unique(m[:, 5].astype(np.float64)).round(2)) == [0.0, 0.1, 0.2]
     assert synth.make_boxes(10, seed=0).shape == (10, 7)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours): stdout carries exactly ONE JSON line with the
+    contract's keys (metric/unit of BASELINE.json, impl, cpu_baseline, e2e with zero copy bytes); anything a native
+    library prints goes to stderr."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from util import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and base["metric"].startswith(d["metric"])
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
