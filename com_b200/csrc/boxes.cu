@@ -183,80 +183,110 @@ __device__ __forceinline__ float iou_from_overlap(const BoxRec& a, const BoxRec&
 }
 
 // ---------------------------------------------------------------- pairwise matrix
-// A block owns a 16 x 128 tile of the (Na, Nb) matrix (2048 pairs, 256 threads).  Two phases:
-//   A. every thread runs the exact far-apart test on 8 consecutive columns of one row, writes the zeros of the tile
-//      with 16-byte stores and appends the pairs that may overlap to a queue in shared memory;
-//   B. the block walks the queue with all lanes busy: the expensive geometry (16 segment crossings, 8 corner tests,
-//      angular sort, shoelace: ~3000 instructions with local-memory arrays) runs only for those pairs.
-// (r1: one thread per pair left every warp with a single near pair — 12 % of the warps of the COMAug 10k x 10k case,
-// where 0.4 % of the pairs overlap — executing the slow path for one lane: 1.55 ms for 400 MB of output.)
-// Tile height TA: 16 rows for small matrices (more blocks than SMs at 500 x 500), 64 rows for large ones — a block
-// pays the latency of one slow-path round however few pairs are queued, so it should own as many pairs as possible.
-constexpr int kTB = 128, kPairsPerThread = 8;
+// Persistent blocks walk 16 x 128 (64 x 128 for large matrices) tiles of the (Na, Nb) matrix.  Per 16-row step:
+//   A. every thread runs the exact far-apart test on 8 consecutive columns of one row, writes the zeros of the step
+//      with 16-byte stores and appends the (i, j) of the pairs that may overlap to a queue in shared memory;
+//   B. whenever the queue holds a whole round (256 pairs) the block evaluates it with EVERY lane busy: the expensive
+//      geometry (16 segment crossings, 8 corner tests, angular sort, shoelace: ~3000 instructions with local-memory
+//      arrays) runs only for queued pairs, and a round is never paid for a handful of them — the queue carries over
+//      from tile to tile and is flushed once at the end.
+// (r1 history on the COMAug 10k x 10k case, 0.4 % of the pairs overlap: one thread per pair 1.55 ms — 12 % of the warps
+// held one near pair and ran the geometry for a single lane; per-tile queues 0.75 ms — every tile still paid one
+// round for its ~55 queued pairs.)
+constexpr int kTB = 128, kPairsPerThread = 8, kRound = 256;
+constexpr int kQueueCap = kRound + 16 * kTB;      // a 16-row step adds at most 16 x 128 pairs to a remainder < 256
+
+template <bool CPUF>
+__device__ __forceinline__ float4 centre_rad(const float* __restrict__ b) {
+  using A = Ar<CPUF>;
+  // the same conservative radius as make_box(): any point of the margin-inflated box is within rad of the centre
+  const float hx = A::add(b[3] / 2, 1e-2f), hy = A::add(b[4] / 2, 1e-2f);
+  return make_float4(b[0], b[1], sqrtf(hx * hx + hy * hy) * 1.01f + 0.02f, 0.0f);
+}
+
+template <bool CPUF>
+__device__ __forceinline__ void eval_pair(const float* __restrict__ boxes_a, const float* __restrict__ trig_a,
+                                          const float* __restrict__ boxes_b, const float* __restrict__ trig_b, int nb,
+                                          int what, uint2 e, float* __restrict__ out) {
+  BoxRec ra, rb;
+  make_box<CPUF>(boxes_a + (size_t)e.x * 7, CPUF ? trig_a + (size_t)e.x * 4 : nullptr, ra);
+  make_box<CPUF>(boxes_b + (size_t)e.y * 7, CPUF ? trig_b + (size_t)e.y * 4 : nullptr, rb);
+  const float ov = overlap_area<CPUF>(ra, rb);
+  out[(size_t)e.x * nb + e.y] = what ? ov : iou_from_overlap<CPUF>(ra, rb, ov);
+}
 
 template <bool CPUF, int kTA>
-__global__ void __launch_bounds__(256) boxes_bev_kernel(const float* __restrict__ boxes_a,
-                                                         const float* __restrict__ trig_a, int na,
-                                                         const float* __restrict__ boxes_b,
-                                                         const float* __restrict__ trig_b, int nb, int what,
-                                                         float* __restrict__ out, int vec_ok) {
-  __shared__ BoxRec sa[kTA], sb[kTB];
-  __shared__ unsigned short queue[kTA * kTB];
+__global__ void __launch_bounds__(kRound) boxes_bev_kernel(const float* __restrict__ boxes_a,
+                                                            const float* __restrict__ trig_a, int na,
+                                                            const float* __restrict__ boxes_b,
+                                                            const float* __restrict__ trig_b, int nb, int what,
+                                                            float* __restrict__ out, int vec_ok, int tiles_x,
+                                                            int ntiles) {
+  static_assert(kTA % 16 == 0 && kTA + kTB <= kRound, "one thread prepares one box of the tile");
+  __shared__ float4 sa[kTA], sb[kTB];       // centre x, y, conservative radius
+  __shared__ uint2 queue[kQueueCap];
   __shared__ int qn;
   const int tid = threadIdx.x;
-  const int a0 = blockIdx.y * kTA, b0 = blockIdx.x * kTB;
   if (tid == 0) qn = 0;
-  static_assert(kTA <= 128 && kTA * kTB <= 65536, "tile must fit the 16-bit queue entries");
-  if (tid < kTB) {
-    const int j = b0 + tid;
-    if (j < nb) make_box<CPUF>(boxes_b + (size_t)j * 7, CPUF ? trig_b + (size_t)j * 4 : nullptr, sb[tid]);
-  } else if (tid < kTB + kTA) {
-    const int i = a0 + tid - kTB;
-    if (i < na) make_box<CPUF>(boxes_a + (size_t)i * 7, CPUF ? trig_a + (size_t)i * 4 : nullptr, sa[tid - kTB]);
-  }
-  __syncthreads();
-  // ---- phase A: far-apart test + zeros
   const int c0 = (tid & 15) * kPairsPerThread;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int a0 = (tile / tiles_x) * kTA, b0 = (tile % tiles_x) * kTB;
+    __syncthreads();                        // the previous tile's readers of sa / sb are done (and qn = 0 is visible)
+    if (tid < kTB) {
+      if (b0 + tid < nb) sb[tid] = centre_rad<CPUF>(boxes_b + (size_t)(b0 + tid) * 7);
+    } else if (tid < kTB + kTA) {
+      if (a0 + tid - kTB < na) sa[tid - kTB] = centre_rad<CPUF>(boxes_a + (size_t)(a0 + tid - kTB) * 7);
+    }
+    __syncthreads();
 #pragma unroll 1
-  for (int r = tid >> 4; r < kTA; r += 16) {
-    const int i = a0 + r;
-    if (i < na && b0 + c0 < nb) {
-      const float ax = sa[r].cx, ay = sa[r].cy, arad = sa[r].rad;
-      unsigned near = 0;
+    for (int r = tid >> 4; r < kTA; r += 16) {           // uniform trip count: every thread reaches the barriers
+      // ---- phase A: far-apart test + zeros for 16 rows x 128 columns
+      const int i = a0 + r;
+      if (i < na && b0 + c0 < nb) {
+        const float4 ra = sa[r];
+        unsigned near = 0;
 #pragma unroll
-      for (int u = 0; u < kPairsPerThread; ++u) {
-        if (b0 + c0 + u < nb) {
-          // the same exact early-out as overlap_area: further apart than the sum of the conservative radii => area +0
-          const float ddx = ax - sb[c0 + u].cx, ddy = ay - sb[c0 + u].cy, rr = arad + sb[c0 + u].rad;
-          if (!(ddx * ddx + ddy * ddy > rr * rr)) near |= 1u << u;
+        for (int u = 0; u < kPairsPerThread; ++u) {
+          if (b0 + c0 + u < nb) {
+            // the same exact early-out as overlap_area: further apart than the sum of the conservative radii => +0
+            const float4 rb = sb[c0 + u];
+            const float ddx = ra.x - rb.x, ddy = ra.y - rb.y, rr = ra.z + rb.z;
+            if (!(ddx * ddx + ddy * ddy > rr * rr)) near |= 1u << u;
+          }
+        }
+        float* o = out + (size_t)i * nb + b0 + c0;
+        if (vec_ok && b0 + c0 + kPairsPerThread <= nb) {
+          reinterpret_cast<float4*>(o)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+          reinterpret_cast<float4*>(o)[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+          for (int u = 0; u < kPairsPerThread; ++u)
+            if (b0 + c0 + u < nb) o[u] = 0.0f;
+        }
+        if (near) {
+          const int base = atomicAdd(&qn, __popc(near));
+          int k = 0;
+#pragma unroll
+          for (int u = 0; u < kPairsPerThread; ++u)
+            if (near & (1u << u)) queue[base + k++] = make_uint2((unsigned)i, (unsigned)(b0 + c0 + u));
         }
       }
-      float* o = out + (size_t)i * nb + b0 + c0;
-      if (vec_ok && b0 + c0 + kPairsPerThread <= nb) {
-        reinterpret_cast<float4*>(o)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        reinterpret_cast<float4*>(o)[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
-#pragma unroll
-        for (int u = 0; u < kPairsPerThread; ++u)
-          if (b0 + c0 + u < nb) o[u] = 0.0f;
-      }
-      if (near) {
-        const int base = atomicAdd(&qn, __popc(near));
-        int k = 0;
-#pragma unroll
-        for (int u = 0; u < kPairsPerThread; ++u)
-          if (near & (1u << u)) queue[base + k++] = (unsigned short)(r * kTB + c0 + u);
-      }
+      // ---- phase B: whole rounds only (taken from the top of the queue)
+      __syncthreads();                      // the pushes (and the zeros) of this step are done
+      const int n = qn;
+      const int take = n & ~(kRound - 1);
+      for (int q = tid; q < take; q += kRound)
+        eval_pair<CPUF>(boxes_a, trig_a, boxes_b, trig_b, nb, what, queue[n - take + q], out);
+      __syncthreads();                      // everybody has read qn and its queue entries
+      if (tid == 0) qn = n - take;
+      __syncthreads();
     }
   }
   __syncthreads();
-  // ---- phase B: the pairs that may overlap (the order of the queue does not matter: one writer per element)
+  // ---- flush: the remainder (< 256 pairs, or everything when the block saw less than one round)
   const int n = qn;
-  for (int q = tid; q < n; q += 256) {
-    const int e = queue[q], rr = e / kTB, cc = e % kTB;
-    const float ov = overlap_area<CPUF>(sa[rr], sb[cc]);
-    out[(size_t)(a0 + rr) * nb + b0 + cc] = what ? ov : iou_from_overlap<CPUF>(sa[rr], sb[cc], ov);
-  }
+  for (int q = tid; q < n; q += kRound)
+    eval_pair<CPUF>(boxes_a, trig_a, boxes_b, trig_b, nb, what, queue[q], out);
 }
 
 // ---------------------------------------------------------------- NMS
@@ -541,16 +571,23 @@ extern "C" int comb_boxes_bev(const float* boxes_a, const float* trig_a, int na,
   const int vec_ok = (nb % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   const bool big = (long long)na * nb >= (4ll << 20);        // enough 64-row tiles to fill the GPU several times
   const int ta = big ? 64 : 16;
-  dim3 grid(cdiv(nb, kTB), cdiv(na, ta));
-  COMB_CHECK_ARG(grid.y <= 65535, "comb_boxes_bev: too many rows (%d)", na);
-  if (flavour == 0 && big)
-    boxes_bev_kernel<true, 64><<<grid, 256, 0, stream>>>(boxes_a, trig_a, na, boxes_b, trig_b, nb, what, out, vec_ok);
-  else if (flavour == 0)
-    boxes_bev_kernel<true, 16><<<grid, 256, 0, stream>>>(boxes_a, trig_a, na, boxes_b, trig_b, nb, what, out, vec_ok);
-  else if (big)
-    boxes_bev_kernel<false, 64><<<grid, 256, 0, stream>>>(boxes_a, trig_a, na, boxes_b, trig_b, nb, what, out, vec_ok);
-  else
-    boxes_bev_kernel<false, 16><<<grid, 256, 0, stream>>>(boxes_a, trig_a, na, boxes_b, trig_b, nb, what, out, vec_ok);
+  const int tiles_x = cdiv(nb, kTB);
+  const long long ntiles = (long long)tiles_x * cdiv(na, ta);
+  COMB_CHECK_ARG(ntiles < (1ll << 31), "comb_boxes_bev: matrix %d x %d too large", na, nb);
+  auto launch = [&](auto kernel) -> int {
+    int per_sm = 0;      // persistent blocks: exactly as many as are resident at once
+    COMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRound, 0));
+    const long long cap = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
+    const int grid = (int)(ntiles < cap ? ntiles : cap);
+    kernel<<<grid, kRound, 0, stream>>>(boxes_a, trig_a, na, boxes_b, trig_b, nb, what, out, vec_ok, tiles_x, (int)ntiles);
+    return COMB_OK;
+  };
+  int rc;
+  if (flavour == 0 && big) rc = launch(boxes_bev_kernel<true, 64>);
+  else if (flavour == 0) rc = launch(boxes_bev_kernel<true, 16>);
+  else if (big) rc = launch(boxes_bev_kernel<false, 64>);
+  else rc = launch(boxes_bev_kernel<false, 16>);
+  if (rc != COMB_OK) return rc;
   COMB_LAUNCH_CHECK();
   return COMB_OK;
 }
