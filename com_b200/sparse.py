@@ -236,8 +236,11 @@ class _SpConvFunctionBF16(torch.autograd.Function):
         din = dw = db = None
         if ctx.needs_input_grad[0]:
             cin_p = ops.pad16(Cin)                       # the kernel's N must be 16 / 32 / 64 / 128: zero rows beyond Cin
-            wt = torch.zeros((cin_p, K, Cout), dtype=torch.float32, device=w3.device)
-            wt[:Cin] = w3.permute(2, 1, 0)
+            if cin_p == Cin:
+                wt = w3.permute(2, 1, 0).contiguous()    # W^T as (Cin, K, Cout): one copy kernel
+            else:
+                wt = torch.zeros((cin_p, K, Cout), dtype=torch.float32, device=w3.device)
+                wt[:Cin] = w3.permute(2, 1, 0)
             din = ops.spconv_fwd_bf16(doutb, ops.pack_weight_bf16(wt), K, cin_p, ctx.scatter_map_fn(),
                                       out_dtype=torch.float32)[:, :Cin].contiguous()
         if ctx.needs_input_grad[1]:
