@@ -61,9 +61,11 @@ SIGNATURES = {
     "comb_dense": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "comb_dense_scatter": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "comb_dense_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "comb_dense_gather": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     "comb_box_trig_host": (None, [_PF, c_int, _PF]),
     "comb_points_in_boxes_mask": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, _P]),
     "comb_points_in_boxes_index": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
+    "comb_points_in_any_box": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, _P]),
     "comb_box_trig4_host": (None, [_PF, c_int, _PF]),
     "comb_boxes_bev": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P]),
     "comb_nms_workspace_bytes": (c_size_t, [c_int]),

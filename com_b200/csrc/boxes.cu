@@ -481,6 +481,49 @@ __global__ void __launch_bounds__(256) pib_mask_kernel(const float* __restrict__
   }
 }
 
+// any-box form of the same test (remove_points_in_boxes3d, pcdet/utils/box_utils.py:117-131, only needs
+// `mask.sum(0) != 0`): one byte per point instead of Nb ints, boxes walked in shared-memory tiles, a thread stops
+// testing a point at its first hit.  Same arithmetic as pib_mask_kernel, so any[p] == OR_b mask[b][p] bit for bit.
+__global__ void __launch_bounds__(256) pib_any_kernel(const float* __restrict__ points, int P, int pstride,
+                                                       const float* __restrict__ boxes,
+                                                       const float* __restrict__ trig, int nb,
+                                                       unsigned char* __restrict__ any) {
+  __shared__ PibBox sb[kPibBoxes];
+  const int p0 = blockIdx.x * (256 * kPibPts) + threadIdx.x;
+  float x[kPibPts], y[kPibPts], z[kPibPts];
+  bool hit[kPibPts];
+#pragma unroll
+  for (int q = 0; q < kPibPts; ++q) {
+    const int p = p0 + q * 256;
+    hit[q] = false;
+    if (p < P) {
+      const float* pp = points + (size_t)p * pstride;
+      x[q] = __ldg(pp); y[q] = __ldg(pp + 1); z[q] = __ldg(pp + 2);
+    } else {
+      x[q] = y[q] = z[q] = 0.f;
+    }
+  }
+  for (int b0 = 0; b0 < nb; b0 += kPibBoxes) {
+    const int nbl = min(kPibBoxes, nb - b0);
+    __syncthreads();
+    if (threadIdx.x < nbl) {
+      const int b = b0 + threadIdx.x;
+      make_pib(boxes + (size_t)b * 7, trig[b * 2], trig[b * 2 + 1], 1e-2f, sb[threadIdx.x]);
+    }
+    __syncthreads();
+    for (int j = 0; j < nbl; ++j) {
+      const PibBox bx = sb[j];
+#pragma unroll
+      for (int q = 0; q < kPibPts; ++q) hit[q] = hit[q] || pt_in_box<true>(x[q], y[q], z[q], bx);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kPibPts; ++q) {
+    const int p = p0 + q * 256;
+    if (p < P) any[p] = hit[q] ? 1 : 0;
+  }
+}
+
 // first-hit index, reference device arithmetic (MARGIN 1e-5, device trig, default contraction)
 __global__ void __launch_bounds__(256) pib_index_kernel(const float* __restrict__ points,
                                                          const float* __restrict__ boxes, int P, int T,
@@ -537,6 +580,22 @@ extern "C" int comb_points_in_boxes_mask(const float* points, int P, int point_s
   dim3 grid(cdiv(P, 256 * kPibPts), cdiv(nb, kPibBoxes));
   COMB_CHECK_ARG(grid.y <= 65535, "comb_points_in_boxes_mask: too many boxes (%d)", nb);
   pib_mask_kernel<<<grid, 256, 0, stream>>>(points, P, point_stride, boxes, box_trig, nb, mask);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}
+
+extern "C" int comb_points_in_any_box(const float* points, int P, int point_stride, const float* boxes,
+                                     const float* box_trig, int nb, unsigned char* any, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(P >= 0 && nb >= 0 && point_stride >= 3, "comb_points_in_any_box: bad shape");
+  if (P == 0) return COMB_OK;
+  COMB_CHECK_ARG(points && any, "comb_points_in_any_box: null pointer");
+  if (nb == 0) {
+    COMB_CUDA(cudaMemsetAsync(any, 0, (size_t)P, stream));
+    return COMB_OK;
+  }
+  COMB_CHECK_ARG(boxes && box_trig, "comb_points_in_any_box: null pointer");
+  pib_any_kernel<<<cdiv(P, 256 * kPibPts), 256, 0, stream>>>(points, P, point_stride, boxes, box_trig, nb, any);
   COMB_LAUNCH_CHECK();
   return COMB_OK;
 }
@@ -623,10 +682,9 @@ extern "C" int comb_nms(const float* boxes, const float* trig, int n, float thre
   COMB_LAUNCH_CHECK();
   const size_t staged = ((size_t)n * cb + cb) * 8;
   if (staged <= 200 * 1024) {
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local DevOnce configured;   // per device: the attribute is a per-device property
+    if (configured.first()) {
       COMB_CUDA(cudaFuncSetAttribute(nms_sweep_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
     }
     nms_sweep_smem_kernel<<<1, 256, staged, stream>>>(mask, n, cb, keep, num_keep);
   } else {

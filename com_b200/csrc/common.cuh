@@ -39,6 +39,21 @@ void count_launch();
   } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// One-time-per-DEVICE guard for cudaFuncSetAttribute (a per-device property): `static thread_local DevOnce once;
+// if (once.first()) cudaFuncSetAttribute(...)`.  A process that drives several GPUs from one thread sets it on each.
+struct DevOnce {
+  unsigned long long seen[2] = {0ull, 0ull};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d < 0 || d >= 128) return true;
+    const unsigned long long bit = 1ull << (d & 63);
+    if (seen[d >> 6] & bit) return false;
+    seen[d >> 6] |= bit;
+    return true;
+  }
+};
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int sm_count();

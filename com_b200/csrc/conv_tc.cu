@@ -484,10 +484,9 @@ int launch_tc(const TcParams& p_in, cudaStream_t stream) {
       break;
     }
   const size_t smem = Cfg::smem_bytes(p.K, p.S);
-  static thread_local bool configured = false;
-  if (!configured) {
+  static thread_local DevOnce configured;   // per device: the attribute is a per-device property
+  if (configured.first()) {
     COMB_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
-    configured = true;
   }
   if (smem > 227 * 1024 - 2048 || Cfg::stages(p.K, p.S) < 2) {
     set_error("comb_spconv_fwd_bf16: shared memory %zu exceeds the per-CTA limit", smem);

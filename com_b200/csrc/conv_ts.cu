@@ -533,11 +533,10 @@ template <int CIN, int COUT>
 int launch_ts(const ConvFwdArgs& p, cudaStream_t stream) {
   using Cfg = TsCfg<CIN, COUT>;
   const size_t smem = Cfg::smem_bytes(p.K);
-  static thread_local bool configured = false;
-  if (!configured) {
+  static thread_local DevOnce configured;   // per device: the attribute is a per-device property
+  if (configured.first()) {
     COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
     COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-    configured = true;
   }
   if (smem > 227 * 1024 - 1024 || (!Cfg::b_resident(p.K) && Cfg::b_stages(p.K) < 2)) {
     set_error("comb_spconv_fwd_bf16: shared memory %zu exceeds the per-CTA limit", smem);

@@ -340,11 +340,10 @@ WgPlan wg_plan(int Cin_p, int Cout, int K, int no_max) {
 
 template <int CIN, int NB>
 int launch_wg(const WgParams& p, const WgPlan& pl, cudaStream_t stream) {
-  static thread_local bool configured = false;
-  if (!configured) {
+  static thread_local DevOnce configured;   // per device: the attribute is a per-device property
+  if (configured.first()) {
     COMB_CUDA(cudaFuncSetAttribute(spconv_wgrad_tc_kernel<CIN, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    227 * 1024 - 2048));
-    configured = true;
   }
   dim3 grid(pl.nchunks, pl.ngroups);
   spconv_wgrad_tc_kernel<CIN, NB><<<grid, kWgThreads, pl.smem, stream>>>(p);

@@ -283,10 +283,9 @@ __global__ void __launch_bounds__(256) wm_pack_kernel(const float* __restrict__ 
 template <int CIN, int COUT>
 int launch_wm(const ConvFwdArgs& p, cudaStream_t stream) {
   const size_t smem = (size_t)p.K * (CIN / 16) * (COUT / 16) * 512 + (size_t)2 * kWarps * p.K * 16 * 4;
-  static thread_local bool configured = false;
-  if (!configured) {
+  static thread_local DevOnce configured;   // per device: the attribute is a per-device property
+  if (configured.first()) {
     COMB_CUDA(cudaFuncSetAttribute(spconv_wm_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    configured = true;
   }
   COMB_CHECK_ARG(smem <= 100 * 1024, "comb_spconv_fwd_bf16: weight image %zu too large for the warp-MMA kernel", smem);
   const int ntiles = cdiv(p.no_max, 16);

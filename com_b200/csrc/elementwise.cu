@@ -248,6 +248,33 @@ __global__ void __launch_bounds__(256) dense_scatter_kernel(const T* __restrict_
   }
 }
 
+// Backward of dense(): grad_feats[row, c] = grad_dense[b, c, z, y, x] (the adjoint of the scatter; cells without a
+// row receive no gradient).  Same thread mapping as dense_scatter_kernel: lanes = consecutive rows (x-neighbours in
+// key order), one 8-channel group per thread, 8 plane reads -> one 16/32-byte row store.
+template <typename T>
+__global__ void __launch_bounds__(256) dense_gather_kernel(const float* __restrict__ dense, const int4* __restrict__ coords,
+                                                            int n_max, const int* __restrict__ n_dev, int batch, int C,
+                                                            int D, int H, int W, T* __restrict__ out) {
+  const int n = eff_n(n_max, n_dev);
+  const int groups = (C + 7) >> 3;
+  const long long total = (long long)groups * ((n + 31) & ~31);
+  const long long DHW = (long long)D * H * W;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)((e >> 5) / groups) * 32 + (int)(e & 31);
+    const int g = (int)((e >> 5) % groups);
+    if (row >= n) continue;
+    const int4 c = __ldg(coords + row);
+    const int c0 = g * 8;
+    const bool ok = (unsigned)c.x < (unsigned)batch && (unsigned)c.y < (unsigned)D && (unsigned)c.z < (unsigned)H &&
+                    (unsigned)c.w < (unsigned)W;
+    const float* o = dense + ((size_t)(ok ? c.x : 0) * C + c0) * DHW + ((size_t)(ok ? c.y : 0) * H + (ok ? c.z : 0)) * W +
+                     (ok ? c.w : 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (c0 + i < C) out[(size_t)row * C + c0 + i] = (T)(ok ? __ldg(o + (size_t)i * DHW) : 0.0f);
+  }
+}
+
 extern "C" size_t comb_dense_workspace_bytes(int batch, int D, int H, int W) {
   if (batch < 1 || D < 1 || H < 1 || W < 1) return 0;
   return align_up((size_t)batch * D * H * W * 4, 256);
@@ -317,6 +344,27 @@ extern "C" int comb_dense_scatter(const void* feats, int dtype, const int* coord
                                                                                 n_max, n_dev, batch, C, D, H, W, out);
   else
     COMB_CHECK_ARG(false, "comb_dense_scatter: unknown dtype %d", dtype);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}
+
+extern "C" int comb_dense_gather(const float* dense, const int* coords, int n_max, const int* n_dev, int batch, int C,
+                                 int D, int H, int W, void* out, int dtype, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(batch >= 1 && C >= 1 && D >= 1 && H >= 1 && W >= 1 && n_max >= 0, "comb_dense_gather: bad shape");
+  if (n_max == 0) return COMB_OK;
+  COMB_CHECK_ARG(dense && coords && out, "comb_dense_gather: null pointer");
+  const long long total = (long long)((C + 7) / 8) * ((n_max + 31) / 32 * 32);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (dtype == COMB_DT_F32)
+    dense_gather_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(dense, (const int4*)coords, n_max, n_dev, batch, C, D,
+                                                                      H, W, (float*)out);
+  else if (dtype == COMB_DT_BF16)
+    dense_gather_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>(dense, (const int4*)coords, n_max, n_dev,
+                                                                               batch, C, D, H, W, (__nv_bfloat16*)out);
+  else
+    COMB_CHECK_ARG(false, "comb_dense_gather: unknown dtype %d", dtype);
   COMB_LAUNCH_CHECK();
   return COMB_OK;
 }

@@ -8,6 +8,7 @@ import ctypes
 
 import numpy as np
 import torch
+import torch.utils.data
 
 from . import _lib
 from ._lib import DT_BF16, DT_F32, EPI_AFFINE, EPI_BIAS, EPI_RELU, EPI_RESIDUAL, check, int3
@@ -15,8 +16,8 @@ from ._lib import DT_BF16, DT_F32, EPI_AFFINE, EPI_BIAS, EPI_RELU, EPI_RESIDUAL,
 __all__ = [
     "voxelize", "mean_vfe", "hash_build", "conv_out_coords", "conv_out_shape", "nbrmap_build",
     "nbrmap_transpose", "nbrmap_to_pairs", "spconv_fwd_f32", "spconv_dgrad_f32", "spconv_wgrad_f32", "spconv_wgrad_bf16",
-    "pack_weight_bf16", "spconv_fwd_bf16", "affine_relu", "cast_pad", "dense", "points_in_boxes_mask",
-    "points_in_boxes_index", "boxes_bev", "nms", "box_trig_host", "box_trig4_host",
+    "pack_weight_bf16", "spconv_fwd_bf16", "affine_relu", "cast_pad", "dense", "dense_gather", "DenseFunction", "points_in_boxes_mask",
+    "points_in_any_box", "points_in_boxes_index", "boxes_bev", "nms", "box_trig_host", "box_trig4_host",
 ]
 
 
@@ -64,6 +65,35 @@ def _need(t, dtype, name):
         raise RuntimeError("%s must be %s, got %s" % (name, dtype, t.dtype))
     if not t.is_contiguous():
         raise RuntimeError("%s must be contiguous" % name)
+
+
+def host_op_device():
+    """Device for the `*_cpu`-named entry points (CPU tensors in and out, arithmetic on the GPU).
+
+    Their reference callers run inside DataLoader worker processes (pcdet/datasets/augmentor/
+    database_sampler_v2.py:600-604, pcdet/utils/box_utils.py:117-131).  Policy:
+      * `spawn` / `forkserver` workers (what the reference selects under --launcher pytorch/slurm,
+        pcdet/utils/common_utils.py:172-173): a CUDA context is created lazily in the worker on its rank's GPU
+        (LOCAL_RANK, else the current device) the first time an op runs;
+      * a worker FORKED from a process that already initialised CUDA cannot use the GPU at all: raise with the remedy
+        instead of dying inside the driver.  There is no CPU fallback."""
+    import os
+    if torch.cuda._is_in_bad_fork():
+        raise RuntimeError(
+            "com_b200: this process was forked from a parent that had already initialised CUDA, so its `*_cpu` box ops "
+            "(points_in_boxes_cpu, boxes_iou_bev_cpu, remove_points_in_boxes3d) cannot reach the GPU.  Start DataLoader "
+            "workers with the 'spawn' start method (DataLoader(..., multiprocessing_context='spawn') or "
+            "torch.multiprocessing.set_start_method('spawn'), which tools/train.py --launcher pytorch already does), or "
+            "run COMAug in the main process (num_workers=0).  com_b200 has no CPU fallback.")
+    if not torch.cuda.is_available():
+        raise RuntimeError("com_b200 box ops need a CUDA device (no CPU fallback)")
+    try:
+        in_worker = torch.utils.data.get_worker_info() is not None
+    except Exception:
+        in_worker = False
+    if in_worker and "LOCAL_RANK" in os.environ:
+        return torch.device("cuda", int(os.environ["LOCAL_RANK"]) % torch.cuda.device_count())
+    return torch.device("cuda", torch.cuda.current_device())
 
 
 def _ws(nbytes, device):
@@ -476,6 +506,35 @@ def dense_scatter(feats, coords, batch, shape, out, n_dev=None):
     return out
 
 
+def dense_gather(grad_dense, coords, dtype=torch.float32, n_dev=None):
+    """Adjoint of dense(): (batch, C, D, H, W) fp32 -> (n, C) rows at `coords`."""
+    lib = _lib.load()
+    _need(grad_dense, torch.float32, "grad_dense")
+    _need(coords, torch.int32, "coords")
+    B, C, D, H, W = [int(v) for v in grad_dense.shape]
+    n = int(coords.shape[0])
+    out = torch.empty((n, C), dtype=dtype, device=grad_dense.device)
+    with _Scope("dense", n=n, C=C, cells=B * D * H * W, in_bytes=4, gather=True):
+        check(lib.comb_dense_gather(_p(grad_dense), _p(coords), n, _p(n_dev), B, C, D, H, W, _p(out), _dt(out), _stream()),
+              "comb_dense_gather")
+    return out
+
+
+class DenseFunction(torch.autograd.Function):
+    """SparseConvTensor.dense() with autograd: forward = comb_dense, backward = comb_dense_gather."""
+
+    @staticmethod
+    def forward(ctx, feats, coords, batch, shape):
+        ctx.save_for_backward(coords)
+        ctx.dtype = feats.dtype
+        return dense(feats.contiguous(), coords, batch, shape)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (coords,) = ctx.saved_tensors
+        return dense_gather(grad.contiguous().float(), coords, dtype=ctx.dtype), None, None, None
+
+
 # --------------------------------------------------------------------------------------------- box ops
 def box_trig_host(boxes_np):
     """(nb,2) float32 = (cosf(-rz), sinf(-rz)) from the host libm (bit-identical to the reference's)."""
@@ -507,6 +566,22 @@ def points_in_boxes_mask(points, boxes, trig, out=None):
         out = torch.empty((nb, P), dtype=torch.int32, device=points.device)
     check(lib.comb_points_in_boxes_mask(_p(points), P, int(points.shape[1]), _p(boxes), _p(trig), nb, _p(out),
                                         _stream()), "comb_points_in_boxes_mask")
+    return out
+
+
+def points_in_any_box(points, boxes, trig, out=None):
+    """points (P, >=3) fp32 CUDA, boxes (Nb,7), trig (Nb,2) -> (P,) uint8: 1 iff the point lies in any box
+    (== (points_in_boxes_mask(...) != 0).any(0), one byte per point instead of Nb ints)."""
+    lib = _lib.load()
+    _need(points, torch.float32, "points")
+    _need(boxes, torch.float32, "boxes")
+    _need(trig, torch.float32, "trig")
+    P, nb = int(points.shape[0]), int(boxes.shape[0])
+    if out is None:
+        out = torch.empty((P,), dtype=torch.uint8, device=points.device)
+    _need(out, torch.uint8, "out")
+    check(lib.comb_points_in_any_box(_p(points), P, int(points.shape[1]), _p(boxes), _p(trig), nb, _p(out),
+                                     _stream()), "comb_points_in_any_box")
     return out
 
 

@@ -118,8 +118,10 @@ def enlarge_box3d(boxes3d, extra_width=(0, 0, 0)):
 
 
 def remove_points_in_boxes3d(points, boxes3d):
-    """Drop every point that lies in any box (COMAug, database_sampler_v2.py:535-539)."""
+    """Drop every point that lies in any box (pcdet/utils/box_utils.py:117-131; COMAug,
+    database_sampler_v2.py:535-539).  Same result as the reference's `points_in_boxes_cpu(...).sum(0) == 0` filter;
+    the (Nb,P) mask is never materialised (comb_points_in_any_box returns one byte per point)."""
     bxs, _ = _to_torch(boxes3d)
     pts, np_in = _to_torch(points)
-    inside_any = points_in_boxes_cpu(pts[:, 0:3], bxs).sum(dim=0) != 0
+    inside_any = _roi.points_in_any_box_cpu(bxs, pts[:, 0:3])
     return _ret(pts[~inside_any], np_in)

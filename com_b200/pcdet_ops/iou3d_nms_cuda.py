@@ -52,13 +52,17 @@ def nms_normal_gpu(boxes, keep, nms_overlap_thresh):
 
 def boxes_iou_bev_cpu(boxes_a_tensor, boxes_b_tensor, ans_iou_tensor):
     """iou3d_cpu.cpp:232-252 — CPU tensors in/out; computed on the GPU with the CPU build's exact
-    arithmetic (host-libm trig tables, no FMA)."""
+    arithmetic (host-libm trig tables, no FMA).  Called from DataLoader workers by COMAug
+    (database_sampler_v2.py:600-604): see ops.host_op_device for the worker-process policy."""
     if not (boxes_a_tensor.is_contiguous() and boxes_b_tensor.is_contiguous()):
         raise RuntimeError("boxes must be contiguous tensor")
+    dev = ops.host_op_device()
     a = boxes_a_tensor.float()
     b = boxes_b_tensor.float()
-    ta = torch.from_numpy(ops.box_trig4_host(a.numpy())).cuda()
-    tb = torch.from_numpy(ops.box_trig4_host(b.numpy())).cuda()
-    out = ops.boxes_bev(a.cuda().contiguous(), b.cuda().contiguous(), flavour="cpu", what="iou", trig_a=ta, trig_b=tb)
-    ans_iou_tensor.copy_(out)
+    with torch.cuda.device(dev):
+        ta = torch.from_numpy(ops.box_trig4_host(a.numpy())).to(dev)
+        tb = torch.from_numpy(ops.box_trig4_host(b.numpy())).to(dev)
+        out = ops.boxes_bev(a.to(dev).contiguous(), b.to(dev).contiguous(), flavour="cpu", what="iou", trig_a=ta,
+                            trig_b=tb)
+        ans_iou_tensor.copy_(out)
     return 1

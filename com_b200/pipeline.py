@@ -129,8 +129,7 @@ class FramePipeline:
         if g is None or g["batch"] != batch or n > g["n_cap"]:
             g = self._capture(points.to(self.device, non_blocking=True), frame_offsets, batch)
         g["points"][:n].copy_(points, non_blocking=True)             # D2D, or H2D straight from pinned memory
-        g["offs_host"][: batch + 1] = torch.tensor(frame_offsets, dtype=torch.int32)
-        g["offs"].copy_(g["offs_host"], non_blocking=True)
+        self._stage_offsets(g, frame_offsets)
         g["graph"].replay()
         self.graph_launches += g["launches"]
         out = self._finish(g["q"], batch)
@@ -151,11 +150,24 @@ class FramePipeline:
         if g is None or g["batch"] != batch or n > g["n_cap"]:
             g = self._capture(points.to(self.device, non_blocking=True), frame_offsets, batch)
         g["points"][:n].copy_(points, non_blocking=True)
-        g["offs_host"][: batch + 1] = torch.tensor(frame_offsets, dtype=torch.int32)
-        g["offs"].copy_(g["offs_host"], non_blocking=True)
+        self._stage_offsets(g, frame_offsets)
         g["graph"].replay()
         self.graph_launches += g["launches"]
         return (g, batch)
+
+    @staticmethod
+    def _stage_offsets(g, frame_offsets):
+        """Frame offsets -> the graph's device buffer through a small RING of pinned staging buffers: a slot is only
+        rewritten after the asynchronous H2D copy that last read it has completed (its event), so steps enqueued back
+        to back without finish() never see each other's offsets."""
+        ring = g["offs_ring"]
+        k = g["offs_k"] % len(ring)
+        g["offs_k"] += 1
+        host, ev = ring[k]
+        ev.synchronize()
+        host[:] = torch.tensor(frame_offsets, dtype=torch.int32)
+        g["offs"].copy_(host, non_blocking=True)
+        ev.record(torch.cuda.current_stream(g["offs"].device))
 
     def finish(self, handle):
         """Read the row counts of the LAST replay of the handle's graph and build the batch_dict (None when a learned
@@ -173,7 +185,9 @@ class FramePipeline:
         g = {"batch": batch, "n_cap": n_cap,
              "points": torch.zeros((n_cap, int(points.shape[1])), dtype=torch.float32, device=points.device),
              "offs": torch.zeros((batch + 1,), dtype=torch.int32, device=points.device),
-             "offs_host": torch.zeros((batch + 1,), dtype=torch.int32).pin_memory()}
+             "offs_ring": [(torch.zeros((batch + 1,), dtype=torch.int32).pin_memory(), torch.cuda.Event())
+                           for _ in range(4)],
+             "offs_k": 0}
         g["points"][:n].copy_(points)
         g["offs"].copy_(torch.tensor(frame_offsets, dtype=torch.int32))
         torch.cuda.synchronize()
@@ -304,12 +318,24 @@ class FrameStream:
         hard = self.pipe.backbone._caps(n1, batch, worst=True)
         if any(c >= caps[li] and caps[li] < hard[li] for c, li in zip(lv[1:], (2, 3, 4, 5))):
             # a learned level capacity overflowed: redo this batch synchronously with worst-case capacities
+            # (on the lane's own launch stream, after everything in flight there); forward_host recaptures the lane's
+            # graph with the capacities learned from this batch, and the lane adopts the new graph and output buffers
             host, offs = lane["src"]
-            lane["pipe"]._graph = None
-            bd = lane["pipe"].forward_host(None, pinned=(host, offs))
-            enc = bd["encoded_spconv_tensor"]
-            return {"features": enc.features.cpu(), "indices": enc.indices.cpu(),
-                    "voxel_counts": bd["voxel_counts"].cpu(), "rows": int(enc.features.shape[0])}
+            with torch.cuda.stream(lane["launch"]):
+                lane["pipe"]._graph = None
+                bd = lane["pipe"].forward_host(None, pinned=(host, offs))
+                enc = bd["encoded_spconv_tensor"]
+                res = {"features": enc.features.cpu(), "indices": enc.indices.cpu(),
+                       "voxel_counts": bd["voxel_counts"].cpu(), "rows": int(enc.features.shape[0])}
+                g = lane["pipe"]._graph
+                if g is not None:
+                    lane["g"] = g
+                    x, c, _ = g["q"]["levels"][-1]
+                    if tuple(x.shape) != tuple(lane["h_feat"].shape):
+                        lane["h_feat"] = torch.empty(tuple(x.shape), dtype=x.dtype).pin_memory()
+                        lane["h_idx"] = torch.empty(tuple(c.shape), dtype=c.dtype).pin_memory()
+                lane["launch"].synchronize()
+            return res
         n = lv[4]
         return {"features": lane["h_feat"][:n], "indices": lane["h_idx"][:n], "voxel_counts": lane["h_cnt"][: batch + 1],
                 "rows": n}

@@ -19,10 +19,11 @@ from . import ops
 
 
 class _Config:
-    # "f32": fp32 check mode (CUDA cores, reference-exact layout of the sum);
-    # "bf16": tensor-core path (bf16 operands, fp32 accumulate): no-grad forward passes, and — with autograd — forward
-    #         dgrad (the same gather-GEMM over the transposed rulebook with W^T) and wgrad on the tcgen05 kernels.
-    compute = os.environ.get("COMB200_COMPUTE", "f32")
+    # "bf16" (default): tensor-core path (bf16 operands, fp32 accumulate; north_star tolerance 2e-2): no-grad forward
+    #         passes, and — with autograd — forward, dgrad (the same gather-GEMM over the transposed rulebook with W^T)
+    #         and wgrad on the tcgen05 kernels.  Channel counts outside {16,32,64,128} fall back to the fp32 kernels.
+    # "f32":  fp32 check mode (CUDA cores, fixed summation order; tolerance 1e-4) — COMB200_COMPUTE=f32.
+    compute = os.environ.get("COMB200_COMPUTE", "bf16")
     # wgrad of the "bf16" training form: "bf16" = tcgen05 kernel (conv_wgrad.cu), "f32" = fp32 check kernel
     wgrad = os.environ.get("COMB200_WGRAD", "bf16")
 
@@ -105,7 +106,12 @@ class SparseConvTensor:
         return self._tables[key]
 
     def dense(self, channels_first=True):
-        out = ops.dense(self.features.contiguous(), self.indices, self.batch_size, self.spatial_shape)
+        # autograd-aware: gradients of the 2D backbone / CenterHead / COMLoss flow back to the rows through
+        # comb_dense_gather (the reference trains through encoded_spconv_tensor.dense(), height_compression.py:21)
+        if torch.is_grad_enabled() and self.features.requires_grad:
+            out = ops.DenseFunction.apply(self.features, self.indices, self.batch_size, self.spatial_shape)
+        else:
+            out = ops.dense(self.features.contiguous(), self.indices, self.batch_size, self.spatial_shape)
         if not channels_first:
             out = out.permute(0, 2, 3, 4, 1).contiguous()
         return out

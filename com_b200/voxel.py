@@ -39,9 +39,8 @@ def _as_cuda_points(pc):
         pc = torch.from_numpy(np.ascontiguousarray(pc, dtype=np.float32))
     if not isinstance(pc, torch.Tensor):
         raise TypeError("points must be a numpy array, a tensorview tensor or a torch tensor")
-    if not torch.cuda.is_available():
-        raise RuntimeError("com_b200 voxelization needs a CUDA device (no CPU fallback)")
-    return pc.to(device="cuda", dtype=torch.float32, non_blocking=True).contiguous()
+    dev = ops.host_op_device()      # worker-process policy: spawn -> lazy context on the rank's GPU, bad fork -> raises
+    return pc.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
 
 
 class Point2VoxelGPU3d:
@@ -67,8 +66,9 @@ class Point2VoxelGPU3d:
     def point_to_voxel(self, pc, clear_voxels=True):
         pts = _as_cuda_points(pc)
         assert pts.shape[1] == self.num_point_features, "num_point_features mismatch"
-        v, c, n = self.point_to_voxel_torch(pts)
-        return TVTensor(v.cpu().numpy()), TVTensor(c.cpu().numpy()), TVTensor(n.cpu().numpy())
+        with torch.cuda.device(pts.device):
+            v, c, n = self.point_to_voxel_torch(pts)
+            return TVTensor(v.cpu().numpy()), TVTensor(c.cpu().numpy()), TVTensor(n.cpu().numpy())
 
 
 class VoxelGeneratorWrapper:

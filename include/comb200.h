@@ -237,6 +237,11 @@ size_t comb_dense_workspace_bytes(int batch, int D, int H, int W);
 int comb_dense_scatter(const void* feats, int dtype, const int* coords, int n_max, const int* n_dev,
                        int batch, int C, int D, int H, int W, float* out, void* stream);
 
+/* Adjoint of dense() for training through HeightCompression (the reference relies on spconv's autograd through
+ * SparseConvTensor.dense(), height_compression.py:21): grad_feats[row, c] = grad_dense[b, c, z, y, x]. */
+int comb_dense_gather(const float* dense, const int* coords, int n_max, const int* n_dev, int batch, int C,
+                      int D, int H, int W, void* grad_feats, int dtype, void* stream);
+
 /* ---- a11/a12: points in boxes -----------------------------------------------------------------
  * comb_points_in_boxes_mask replaces points_in_boxes_cpu (pcdet/ops/roiaware_pool3d/src/
  * roiaware_pool3d.cpp:143-168, MARGIN 1e-2): mask[b*P + p] = 1 iff point p lies in box b.
@@ -253,6 +258,12 @@ int comb_points_in_boxes_mask(const float* points, int P, int point_stride, cons
                               const float* box_trig, int nb, int* mask, void* stream);
 int comb_points_in_boxes_index(const float* points, const float* boxes, int batch, int P, int T,
                                int* idx, void* stream);
+/* comb_points_in_any_box: any[p] = 1 iff point p lies in at least one box (P bytes) — the only thing
+ * remove_points_in_boxes3d (pcdet/utils/box_utils.py:117-131) and COMAug's point removal
+ * (pcdet/datasets/augmentor/database_sampler_v2.py:535-539) use of the (Nb,P) mask: `mask.sum(0) != 0`.
+ * Same arithmetic and box_trig contract as comb_points_in_boxes_mask. */
+int comb_points_in_any_box(const float* points, int P, int point_stride, const float* boxes,
+                           const float* box_trig, int nb, unsigned char* any, void* stream);
 
 /* ---- a13/a14: rotated BEV IoU -----------------------------------------------------------------
  * flavour 0 ("cpu"): replaces boxes_iou_bev_cpu (pcdet/ops/iou3d_nms/src/iou3d_cpu.cpp:232-252);

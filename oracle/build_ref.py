@@ -33,11 +33,14 @@ def build(verbose=False):
         os.makedirs(bdir, exist_ok=True)
         load(name=name, sources=[os.path.join(REF, "pcdet", "ops", s) for s in srcs], extra_cflags=["-O2"],
              extra_cuda_cflags=["-O2"], build_directory=bdir, verbose=verbose)
+    from . import ref_py
+    ref_py.build_pyc()          # byte-code of the reference's hot-path Python modules (see ref_py.py)
     return True
 
 
 def available():
-    return all(os.path.exists(os.path.join(OUT, n, n + ".so")) for n in MODS)
+    from . import ref_py
+    return all(os.path.exists(os.path.join(OUT, n, n + ".so")) for n in MODS) and ref_py.pyc_available()
 
 
 def load_ref(name):
@@ -53,5 +56,8 @@ def load_ref(name):
 
 
 if __name__ == "__main__":
+    sys.path.insert(0, os.path.dirname(HERE))
+    __package__ = "oracle"
+    import oracle  # noqa: F401
     ok = build(verbose="-v" in sys.argv)
     print("built" if ok else "reference tree not found; nothing built", OUT)

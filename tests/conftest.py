@@ -29,3 +29,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _fp32_check_mode_by_default():
+    """Tests run the module path in the fp32 CHECK arithmetic (1e-4 bar) unless they select the bf16 tensor-core form
+    themselves (the product default is bf16, com_b200/sparse.py)."""
+    from com_b200 import sparse
+    old = (sparse.config.compute, sparse.config.wgrad)
+    sparse.config.compute = "f32"
+    yield
+    sparse.config.compute, sparse.config.wgrad = old

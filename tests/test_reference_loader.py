@@ -1,0 +1,75 @@
+"""CPU checks of the machinery that runs the reference's own Python on the drop-ins (oracle/ref_py.py +
+com_b200.install_dropins): imports resolve to the mirrors, post-import hooks patch the reference classes, the
+byte-code build works without the source tree.  The numerical tests of the same modules are the -m gpu tests in
+test_gpu_reference_dropin.py."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import ref_py
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(not ref_py.available(), reason="reference Python not available")
+
+
+def test_reference_modules_resolve_to_dropins():
+    reg = ref_py.registry()
+    sb = ref_py.load("pcdet.models.backbones_3d.spconv_backbone")
+    from com_b200 import models, sparse
+    assert sb.spconv.SubMConv3d is sparse.SubMConv3d and sb.spconv.SparseConvTensor is sparse.SparseConvTensor
+    cls = reg["backbones_3d"].__all__["VoxelResBackBone8x"]
+    assert cls.__module__ == "pcdet.models.backbones_3d.spconv_backbone" and cls._comb_fused_patch
+    bb = cls(ref_py.EasyDict(NAME="VoxelResBackBone8x"), 5, np.array([1504, 1504, 40]))
+    assert isinstance(bb.conv_input[0], sparse.SubMConv3d) and models._fusable(bb)
+    assert [int(v) for v in bb.sparse_shape] == [41, 1504, 1504] and bb.out_spatial_shape() == [2, 188, 188]
+    mirror = models.VoxelResBackBone8x(None, 5, [1504, 1504, 40])
+    assert list(bb.state_dict().keys()) == list(mirror.state_dict().keys())
+    assert all(a.shape == b.shape for a, b in zip(bb.state_dict().values(), mirror.state_dict().values()))
+    # spconv_utils.find_all_spconv_keys (spconv_utils.py:10-25) sees the conv weights by name
+    su = ref_py.load("pcdet.utils.spconv_utils")
+    keys = su.find_all_spconv_keys(bb)
+    assert "conv_input.0.weight" in keys and "conv_out.0.weight" in keys and len(keys) == 21
+    # non-residual backbone of the same file: not fusable, keeps the reference forward
+    vb = reg["backbones_3d"].__all__["VoxelBackBone8x"](ref_py.EasyDict(), 5, np.array([1504, 1504, 40]))
+    assert not models._fusable(vb)
+    iou = ref_py.load("pcdet.ops.iou3d_nms.iou3d_nms_utils")
+    roi = ref_py.load("pcdet.ops.roiaware_pool3d.roiaware_pool3d_utils")
+    assert iou.iou3d_nms_cuda.__name__ == "com_b200.pcdet_ops.iou3d_nms_cuda"
+    assert roi.roiaware_pool3d_cuda.__name__ == "com_b200.pcdet_ops.roiaware_pool3d_cuda"
+    bu = ref_py.load("pcdet.utils.box_utils")
+    assert bu.remove_points_in_boxes3d._comb and callable(bu.remove_points_in_boxes3d.reference)
+    dp = ref_py.load("pcdet.datasets.processor.data_processor")
+    from com_b200 import voxel
+    assert dp.tv.from_numpy is voxel.from_numpy      # the generator class itself is imported lazily (data_processor.py:17-26)
+    assert "CurriculumCenterHead_x5" in reg["dense_heads"].__all__
+    assert ref_py.load("pcdet.models.detectors.centerpoint").CenterPoint.__name__ == "CenterPoint"
+
+
+def test_cpu_tensors_raise_no_fallback():
+    """Without a GPU the `*_cpu` entry points raise — there is no host implementation behind them."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without CUDA")
+    iou = ref_py.load("pcdet.ops.iou3d_nms.iou3d_nms_utils")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        iou.boxes_bev_iou_cpu(np.zeros((2, 7), np.float32), np.zeros((2, 7), np.float32))
+
+
+def test_bytecode_build_loads_without_source_tree():
+    if not ref_py.source_available():
+        pytest.skip("byte-code is built where the reference tree is mounted")
+    assert ref_py.build_pyc() >= 19
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from oracle import ref_py\n"
+            "assert not ref_py.source_available() and ref_py.pyc_available()\n"
+            "reg = ref_py.registry()\n"
+            "m = ref_py.load('pcdet.models.backbones_3d.spconv_backbone')\n"
+            "assert m.__file__.endswith('.pyc') and m.VoxelResBackBone8x._comb_fused_patch\n"
+            "assert 'CurriculumCenterHead_x5' in reg['dense_heads'].__all__\n"
+            "print('ok')\n" % ROOT)
+    env = dict(os.environ, COM_REFERENCE="/nonexistent")
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
