@@ -135,7 +135,9 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
-template <int CIN, int COUT, bool TRACE>
+// PIPE: software-pipelined gather (two batches of loads in flight per gather warp, register budget moved to the gather
+// warps with setmaxnreg); PIPE = false is the r1 loop (one batch in flight), kept for A/B runs (COMB_TS_PIPE=0).
+template <int CIN, int COUT, bool TRACE, bool PIPE>
 __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   using Cfg = TsCfg<CIN, COUT>;
   extern __shared__ uint8_t smem_raw[];
@@ -216,7 +218,116 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bars + kTmemSlot) : "memory");
   if (TRACE && tid == 0) dbg_cta_time(p.dbg, 1);
 
-  if (warp < kGatherWarps) {
+  if (PIPE) {
+    // Register budget: the CTA owns 768 x 80 = 61440 registers for its whole life (setmaxnreg only moves registers
+    // inside the CTA's pool: asking for more than the other warpgroups release never completes — r2 lesson, a 104-register
+    // request deadlocked).  The gather warps (warpgroups 0-3) hold two batches of 32 registers of loads in flight; the
+    // epilogue warpgroup gives up 16 and the MMA / weight / index warpgroup 48 registers per thread:
+    // 512 x 96 + 128 x 64 + 128 x 32 = 61440.
+    if (warp < kGatherWarps) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;" ::: "memory");
+    else if (warp < kEpiWarp0 + 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
+  }
+
+  if (PIPE && warp < kGatherWarps) {
+    // ===================== gather, software pipelined =====================
+    // Same work split as below (group g = chunk sub-slot g of every stage, warp q of the group = row quarter q), but
+    // the loads of iteration j+1 are issued BEFORE the rows of iteration j are stored to tensor memory, so every warp
+    // has up to two batches of 8 x 16-byte loads in flight and the load latency (r1 trace: 300-700 cycles of every
+    // ~1100-cycle iteration) overlaps the slot wait, the register shuffle and tcgen05.st of the previous batch.
+    const int q = warp & 3, grp = warp >> 2;
+    const int j = lane & 3, r8 = lane >> 2;
+    int slot0, slot1, eo0, eo1;
+    if (CIN <= 64) {
+      slot0 = (8 * j) / CIN;
+      eo0 = (8 * j) % CIN;
+      slot1 = (32 + 8 * j) / CIN;
+      eo1 = (32 + 8 * j) % CIN;
+    } else {
+      slot0 = slot1 = 0;
+      eo0 = 8 * j;
+      eo1 = 32 + 8 * j;
+    }
+    const __nv_bfloat16* in = p.in;
+    const int t = grp & (T - 1);
+    const uint32_t row_off = (uint32_t)(q * 32 + r8) * 4;           // + (h*16 + rr*8)*4 per row of the thread
+    const uint32_t ta0 = tmem_base + ((uint32_t)(q * 32) << 16) + colA + (uint32_t)(grp * 32);
+    const int total = my_super * nst;
+
+    // load side: iteration cursor (pass lit, stage lst) ; store side: (pass sit, stage sst) + TMEM stage ring (s, ph)
+    int lit = 0, lst = 0, lj = 0;
+    uint32_t l_idx_tile = 0;
+    bool l_absent = false;
+    auto issue = [&](uint4 (&v)[2][2][2]) -> bool {
+      if (lst == 0) {                                 // first stage of a pass: its index tile must have landed
+        const int n = (lit << lT) + t;
+        const int buf = n & (NI - 1);
+        l_absent = t == 1 && (int)blockIdx.x + lit * (int)gridDim.x >= nfull;
+        l_idx_tile = idx_base + (uint32_t)buf * idx_buf_bytes;
+        mbar_wait_sleep(bars + kBarIdx + 8 * buf, (uint32_t)(n >> lNI) & 1u);
+      }
+      const int c = 2 * lst + (grp >> 1);
+      const bool have = c < nchunks && !l_absent;
+      if (have) {
+        const uint32_t idx_c = l_idx_tile + row_off +
+                               (uint32_t)(CIN <= 64 ? c * Cfg::kOffPerChunk : c / Cfg::kChunksPerOff) * kBM * 4;
+        const int ehalf = CIN > 64 ? (c % Cfg::kChunksPerOff) * 64 : 0;
+        const __nv_bfloat16* src0 = in + ehalf + eo0;
+        const __nv_bfloat16* src1 = in + ehalf + eo1;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            int rw0, rw1;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw0) : "r"(idx_c + (uint32_t)(slot0 * kBM + h * 16 + rr * 8) * 4) : "memory");
+            if (CIN <= 32) {
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw1) : "r"(idx_c + (uint32_t)(slot1 * kBM + h * 16 + rr * 8) * 4) : "memory");
+            } else {
+              rw1 = rw0;
+            }
+            v[h][rr][0] = make_uint4(0u, 0u, 0u, 0u);
+            v[h][rr][1] = make_uint4(0u, 0u, 0u, 0u);
+            if (rw0 >= 0) v[h][rr][0] = __ldg(reinterpret_cast<const uint4*>(src0 + (size_t)(uint32_t)rw0 * CIN));
+            if (rw1 >= 0) v[h][rr][1] = __ldg(reinterpret_cast<const uint4*>(src1 + (size_t)(uint32_t)rw1 * CIN));
+          }
+      }
+      ++lj;
+      if (++lst == nst) { lst = 0; ++lit; }
+      return have;
+    };
+    int s = 0, sit = 0, sst = 0;
+    uint32_t ph = 0;
+    auto store = [&](const uint4 (&v)[2][2][2], bool have) {
+      mbar_wait_sleep(bars + kBarEmpty + 8 * s, ph ^ 1u);
+      if (have) {
+        tc_fence_after();
+        const uint32_t ta = ta0 + (uint32_t)(s * 128);
+        tmem_st_16x256b_x4(ta, v[0][0][0], v[0][1][0], v[0][0][1], v[0][1][1]);
+        tmem_st_16x256b_x4(ta + (16u << 16), v[1][0][0], v[1][1][0], v[1][0][1], v[1][1][1]);
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      if (lane == 0) mbar_arrive(bars + kBarFull + 8 * s);
+      if (++s == NS) { s = 0; ph ^= 1u; }
+      if (++sst == nst) {                             // all index reads of this pass were issued one iteration ago
+        __syncwarp();
+        if (lane == 0)
+          for (int tt = 0; tt < T; ++tt) mbar_arrive(bars + kBarIdxFree + 8 * (((sit << lT) + tt) & (NI - 1)));
+        sst = 0;
+        ++sit;
+      }
+    };
+    uint4 va[2][2][2], vb[2][2][2];
+    bool ha = false, hb = false;
+    if (total > 0) ha = issue(va);
+    for (int jj = 0; jj < total; jj += 2) {
+      if (lj < total) hb = issue(vb);
+      store(va, ha);
+      if (jj + 1 >= total) break;
+      if (lj < total) ha = issue(va);
+      store(vb, hb);
+    }
+  } else if (warp < kGatherWarps) {
     // ===================== gather: global/L2 -> registers -> TMEM =====================
     // group g (4 warps, one per row quarter) fills chunk sub-slot g of every stage
     const int q = warp & 3, grp = warp >> 2;
@@ -529,14 +640,24 @@ __global__ void __launch_bounds__(256) ts_pack_kernel(const float* __restrict__ 
   }
 }
 
+static bool ts_pipe() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("COMB_TS_PIPE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int CIN, int COUT>
 int launch_ts(const ConvFwdArgs& p, cudaStream_t stream) {
   using Cfg = TsCfg<CIN, COUT>;
   const size_t smem = Cfg::smem_bytes(p.K);
   static thread_local DevOnce configured;   // per device: the attribute is a per-device property
   if (configured.first()) {
-    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
   }
   if (smem > 227 * 1024 - 1024 || (!Cfg::b_resident(p.K) && Cfg::b_stages(p.K) < 2)) {
     set_error("comb_spconv_fwd_bf16: shared memory %zu exceeds the per-CTA limit", smem);
@@ -544,8 +665,9 @@ int launch_ts(const ConvFwdArgs& p, cudaStream_t stream) {
   }
   const int nsuper = cdiv(cdiv(p.no_max, kBM), Cfg::tiles_per_pass(p.K));
   const int grid = nsuper < sm_count() ? nsuper : sm_count();
-  if (p.dbg != nullptr) spconv_ts_kernel<CIN, COUT, true><<<grid, kThreads, smem, stream>>>(p);   // pipeline trace build
-  else spconv_ts_kernel<CIN, COUT, false><<<grid, kThreads, smem, stream>>>(p);
+  if (p.dbg != nullptr) spconv_ts_kernel<CIN, COUT, true, false><<<grid, kThreads, smem, stream>>>(p);   // pipeline trace build
+  else if (ts_pipe()) spconv_ts_kernel<CIN, COUT, false, true><<<grid, kThreads, smem, stream>>>(p);
+  else spconv_ts_kernel<CIN, COUT, false, false><<<grid, kThreads, smem, stream>>>(p);
   COMB_LAUNCH_CHECK();
   return COMB_OK;
 }

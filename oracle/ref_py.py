@@ -9,7 +9,7 @@ therefore
   * serves `pcdet.<a>.<b>` from the reference tree BY FILE PATH, treating every directory as an empty namespace
     package (the reference's package `__init__.py` files are not executed), and
   * on the GPU box, where /root/reference does not exist, serves the same modules from byte-code compiled here by
-    `build_pyc()` into oracle/_ref/pcdet_pyc/ (git-ignored like the compiled C++ reference next to it; produced from
+    `build_pyc()` into oracle/_ref/pcdet_bc/ (git-ignored like the compiled C++ reference next to it; produced from
     the sources where they lie, no reference source is copied into the repository).
 
 Registries that the skipped `__init__`s would have defined (`backbones_3d.__all__` ...) are synthesised by
@@ -26,7 +26,7 @@ import types
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("COM_REFERENCE", "/root/reference")
-PYC_ROOT = os.path.join(HERE, "_ref", "pcdet_pyc")
+PYC_ROOT = os.path.join(HERE, "_ref", "pcdet_bc")      # byte-code files are named *.bc: *.pyc is filtered out of gpurun snapshots
 
 
 def source_available():
@@ -34,7 +34,7 @@ def source_available():
 
 
 def pyc_available():
-    return os.path.exists(os.path.join(PYC_ROOT, "pcdet", "models", "backbones_3d", "spconv_backbone.pyc"))
+    return os.path.exists(os.path.join(PYC_ROOT, "pcdet", "models", "backbones_3d", "spconv_backbone.bc"))
 
 
 def available():
@@ -68,13 +68,13 @@ EXTRA_PACKAGES = ["pcdet/models/backbones_3d/pfe", "pcdet/models/roi_heads"]
 
 
 def build_pyc():
-    """Byte-compile MODULES from the reference tree into oracle/_ref/pcdet_pyc (no-op without /root/reference)."""
+    """Byte-compile MODULES from the reference tree into oracle/_ref/pcdet_bc (no-op without /root/reference)."""
     if not source_available():
         return False
     import warnings
     n = 0
     for rel in MODULES:
-        dst = os.path.join(PYC_ROOT, rel + "c")
+        dst = os.path.join(PYC_ROOT, rel[:-3] + ".bc")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore", SyntaxWarning)
@@ -163,7 +163,7 @@ class _RefFinder(importlib.abc.MetaPathFinder):
         if source_available():
             roots.append((REF, ".py", importlib.machinery.SourceFileLoader))
         if pyc_available():
-            roots.append((PYC_ROOT, ".pyc", importlib.machinery.SourcelessFileLoader))
+            roots.append((PYC_ROOT, ".bc", importlib.machinery.SourcelessFileLoader))
         for root, ext, loader_cls in roots:
             f = os.path.join(root, rel + ext)
             if os.path.isfile(f):

@@ -1,7 +1,7 @@
 """The REFERENCE's own Python, unmodified, executed on top of the drop-ins (com_b200.install_dropins()).
 
 What runs here is the reference code itself (loaded by oracle/ref_py.py from /root/reference when it is mounted,
-else from the byte-code built into oracle/_ref/pcdet_pyc): pcdet/models/backbones_3d/spconv_backbone.py
+else from the byte-code built into oracle/_ref/pcdet_bc): pcdet/models/backbones_3d/spconv_backbone.py
 (VoxelResBackBone8x through the registry dictionary), vfe/mean_vfe.py, map_to_bev/height_compression.py,
 pcdet/ops/iou3d_nms/iou3d_nms_utils.py, pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py,
 pcdet/utils/box_utils.py, pcdet/datasets/processor/data_processor.py and
@@ -19,7 +19,7 @@ from com_b200 import models, pipeline, sparse, synth
 from oracle import build_ref, cpu_pipeline, ref_py
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not ref_py.available(), reason="reference Python not available (oracle/_ref/pcdet_pyc)")]
+              pytest.mark.skipif(not ref_py.available(), reason="reference Python not available (oracle/_ref/pcdet_bc)")]
 
 RANGE, VSIZE = [-12.8, -12.8, -2.0, 12.8, 12.8, 4.0], [0.1, 0.1, 0.15]      # grid 256 x 256 x 40
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "box_ops_ref.npz")

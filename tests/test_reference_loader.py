@@ -67,7 +67,7 @@ def test_bytecode_build_loads_without_source_tree():
             "assert not ref_py.source_available() and ref_py.pyc_available()\n"
             "reg = ref_py.registry()\n"
             "m = ref_py.load('pcdet.models.backbones_3d.spconv_backbone')\n"
-            "assert m.__file__.endswith('.pyc') and m.VoxelResBackBone8x._comb_fused_patch\n"
+            "assert m.__file__.endswith('.bc') and m.VoxelResBackBone8x._comb_fused_patch\n"
             "assert 'CurriculumCenterHead_x5' in reg['dense_heads'].__all__\n"
             "print('ok')\n" % ROOT)
     env = dict(os.environ, COM_REFERENCE="/nonexistent")
