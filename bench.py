@@ -464,12 +464,19 @@ def train_leg(torch, frames, world=1, local_rank=0):
                        "batch 2 per GPU (module path with autograd)%s" % (
                            ", torch DDP over %d GPUs (NCCL gradient all-reduce)" % world if world > 1 else ""),
            "n_gpus": world}
+    res["workload"] = res["workload"].replace("(module path with autograd)", "(module path with autograd, and the fused "
+                                              "train-mode step of com_b200/train.py)")
     old = (sparse.config.compute, sparse.config.wgrad)
     try:
         for compute, wgrad, label, reps in (("f32", "f32", "fp32_check", 2),
                                             ("bf16", "f32", "bf16_fwd_dgrad_tcgen05_wgrad_fp32", 2),
-                                            ("bf16", "bf16", "bf16_fwd_dgrad_wgrad_tcgen05", 10)):
+                                            ("bf16", "bf16", "bf16_fwd_dgrad_wgrad_tcgen05", 10),
+                                            ("bf16", "bf16", "fused_train_step", 20)):
             sparse.config.compute, sparse.config.wgrad = compute, wgrad
+            # "fused_train_step": com_b200/train.py — key-ordered rows, bitmap rulebooks, BatchNorm batch statistics /
+            # ReLU / residual and their backward in libcomb200 kernels, W and W^T packed once per optimizer step; the
+            # other three labels are the module path (every conv / BatchNorm1d / ReLU called one by one under autograd)
+            net.fused = label == "fused_train_step"
             step()
             step()
             cdist.barrier()
@@ -498,6 +505,7 @@ def train_leg(torch, frames, world=1, local_rank=0):
 
         cap = _Capture()
         sparse.config.compute, sparse.config.wgrad = "bf16", "bf16"
+        net.fused = True                    # the wgrad launches of the fused step (key-ordered rows)
         ops.set_profiler(cap)
         try:
             step()

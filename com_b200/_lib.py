@@ -58,6 +58,12 @@ SIGNATURES = {
     "comb_debug_conv_trace": (c_int, [_P]),
     "comb_affine_relu": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, _P, c_int, _P, _P]),
     "comb_cast_pad": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P]),
+    "comb_bn_workspace_bytes": (c_size_t, [c_int]),
+    "comb_bn_train_fwd": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, c_float, c_float, _P, _P, _P, c_int, _P, _P, _P, _P,
+                                  c_size_t, _P]),
+    "comb_bn_train_bwd": (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, _P, _P, _P, c_int, _P, _P, _P, _P, _P, c_size_t,
+                                  _P]),
+    "comb_col_sum": (c_int, [_P, c_int, _P, c_int, _P, _P, c_size_t, _P]),
     "comb_dense": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "comb_dense_scatter": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "comb_dense_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

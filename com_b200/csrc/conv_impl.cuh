@@ -24,6 +24,9 @@ struct ConvFwdArgs {
   void* out;
   int out_f32;
   long long* dbg;   // optional trace buffer (comb_debug_conv_trace), NULL in production
+  int blocked = 0;  // conv_ts: contiguous super-tile range per CTA (1) or strided assignment (0, default)
+  int ni = 4;       // conv_ts: index-tile ring depth (set by launch_ts)
+  int nb = 0;       // conv_ts: streamed-weight stages (set by launch_ts)
 };
 
 int ts_fwd_bf16(const ConvFwdArgs& p, int Cin_p, int Cout, cudaStream_t stream);

@@ -137,7 +137,7 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 
 // PIPE: software-pipelined gather (two batches of loads in flight per gather warp, register budget moved to the gather
 // warps with setmaxnreg); PIPE = false is the r1 loop (one batch in flight), kept for A/B runs (COMB_TS_PIPE=0).
-template <int CIN, int COUT, bool TRACE, bool PIPE>
+template <int CIN, int COUT, bool TRACE, int PIPE>
 __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   using Cfg = TsCfg<CIN, COUT>;
   extern __shared__ uint8_t smem_raw[];
@@ -151,30 +151,56 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   const int kpad = Cfg::k_pad(K);
   const bool bres = Cfg::b_resident(K);
   constexpr int T = 2, lT = 1;                       // row tiles per pass (256 rows): one per MMA-issuing thread
-  const int NI = Cfg::n_idx(K);                      // index-tile buffers (8 or 4)
+  const int NI = p.ni;                               // index-tile buffers (8 or 4), chosen on the host (launch_ts)
   const int lNI = NI == 8 ? 3 : 2;
-  const int NB = Cfg::b_stages(K);
+  const int NB = p.nb;                               // streamed-weight stages, chosen on the host
   const int ND = Cfg::n_acc(K);                      // accumulator ring (power of two, >= T)
   const int NS = Cfg::a_stages(K);                   // A stages of 4 chunks
   const uint32_t colA = (uint32_t)Cfg::d_cols(K);
   // Passes.  A pass walks T row tiles; with T = 2 the last wave of passes is split into single-tile passes when
   // that shortens it (r <= grid/2 leftover super-tiles become 2r half passes on 2r CTAs: the absent second tile
   // is neither gathered nor multiplied).
+  // Two assignments of super-tiles (pairs of row tiles) to CTAs:
+  //  * strided (default): CTA b owns b, b+grid, ...;
+  //  * blocked (COMB_TS_BLOCKED=1): CTA b owns a CONTIGUOUS run of super-tiles — with rows in key order the tiles of one
+  //    CTA are spatial neighbours in the same z-plane, so the rows a tile gathers for its dy = +1 taps are the rows the
+  //    next tile gathers for dy = 0, -1 and could still be in the SM's L1.  r2 A/B on the bench frames: 0.94-0.96 ms
+  //    per step against 0.93 strided, with 8 or 4 index buffers and 8, 4 or 2 weight stages (i.e. 0-100 KB of L1):
+  //    cross-tile L1 reuse does not bound the gather.  Kept as a switch.
   int nsuper = (ntiles + T - 1) >> lT, nfull = nsuper;
+  const bool blocked = p.blocked != 0;
   {
+    // the last wave of passes is split into single-tile passes when that shortens it (r <= grid/2 leftover super-tiles
+    // become 2r half passes on 2r CTAs: the absent second tile is neither gathered nor multiplied)
     const int r = nsuper % (int)gridDim.x;
     if (T == 2 && r > 0 && 2 * r <= (int)gridDim.x) {
       nfull = nsuper - r;
       nsuper = nfull + (ntiles - 2 * nfull);
     }
   }
+  // blocked: the nfull full super-tiles are dealt out in contiguous runs (base or base+1 per CTA), the half passes of
+  // the split last wave go one each to the first CTAs
+  const int base = nfull / (int)gridDim.x, rem = nfull % (int)gridDim.x;
+  const int b_lo = (int)blockIdx.x * base + ((int)blockIdx.x < rem ? (int)blockIdx.x : rem);
+  const int b_cnt = base + ((int)blockIdx.x < rem ? 1 : 0);
+  // super-tile of pass `it` of this CTA (>= nfull: a single-tile pass), and whether its second row tile is absent
+  auto sidx_of = [&](int it) -> int {
+    if (!blocked) return (int)blockIdx.x + it * (int)gridDim.x;
+    return it < b_cnt ? b_lo + it : nfull + (int)blockIdx.x;
+  };
+  auto absent_of = [&](int it) -> bool { return sidx_of(it) >= nfull || 2 * sidx_of(it) + 1 >= ntiles; };
   // row tile of tile-sequence number n of this CTA (a tile index past the end reads as "no rows")
   auto tile_of = [&](int n) -> int {
-    const int sidx = (int)blockIdx.x + (n >> lT) * (int)gridDim.x;
+    const int sidx = sidx_of(n >> lT);
     if (sidx < nfull) return (sidx << lT) + (n & (T - 1));
     return (n & (T - 1)) == 0 ? (nfull << lT) + (sidx - nfull) : 0x00FFFFFF;
   };
-  const int my_super = nsuper > (int)blockIdx.x ? (nsuper - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  int my_super;
+  if (blocked) {
+    my_super = b_cnt + ((int)blockIdx.x < nsuper - nfull ? 1 : 0);
+  } else {
+    my_super = nsuper > (int)blockIdx.x ? (nsuper - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  }
   const int CT = nchunks << lT;                      // chunk slots per super-tile, order (c, t)
   const int nst = (CT + 3) >> 2;                     // stages per super-tile (the last one may be partial)
 
@@ -229,40 +255,34 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
   }
 
-  if (PIPE && warp < kGatherWarps) {
+  if (PIPE == 1 && warp < kGatherWarps) {
     // ===================== gather, software pipelined =====================
     // Same work split as below (group g = chunk sub-slot g of every stage, warp q of the group = row quarter q), but
     // the loads of iteration j+1 are issued BEFORE the rows of iteration j are stored to tensor memory, so every warp
-    // has up to two batches of 8 x 16-byte loads in flight and the load latency (r1 trace: 300-700 cycles of every
-    // ~1100-cycle iteration) overlaps the slot wait, the register shuffle and tcgen05.st of the previous batch.
+    // has up to two batches of loads in flight and the load latency (r1 trace: 300-700 cycles of every ~1100-cycle
+    // iteration) overlaps the slot wait and the tcgen05.st of the previous batch.
+    // Loads are 8 bytes wide and land DIRECTLY in the registers of the tcgen05.st.16x256b fragment (thread t, repeat
+    // g: registers 4g, 4g+1 = bytes 32g + 8(t%4) .. +7 of row t/4, registers 4g+2, 4g+3 = the same bytes of row
+    // t/4 + 8): no staging registers and no register moves, and K keeps its natural order (the weight image of this
+    // variant is packed without the permutation).  r2 measurement of the first pipelined version (16-byte loads +
+    // staging block): 96 registers were not enough, ~20 spill instructions per iteration went to L2 (the shared memory
+    // carve-out leaves no L1 at 64x64: 2.9 M local-load sector misses) and the kernel was 1.6x SLOWER.
     const int q = warp & 3, grp = warp >> 2;
     const int j = lane & 3, r8 = lane >> 2;
-    int slot0, slot1, eo0, eo1;
-    if (CIN <= 64) {
-      slot0 = (8 * j) / CIN;
-      eo0 = (8 * j) % CIN;
-      slot1 = (32 + 8 * j) / CIN;
-      eo1 = (32 + 8 * j) % CIN;
-    } else {
-      slot0 = slot1 = 0;
-      eo0 = 8 * j;
-      eo1 = 32 + 8 * j;
-    }
-    const __nv_bfloat16* in = p.in;
+    const __nv_bfloat16* in = p.in + 4 * j;
     const int t = grp & (T - 1);
     const uint32_t row_off = (uint32_t)(q * 32 + r8) * 4;           // + (h*16 + rr*8)*4 per row of the thread
     const uint32_t ta0 = tmem_base + ((uint32_t)(q * 32) << 16) + colA + (uint32_t)(grp * 32);
     const int total = my_super * nst;
 
-    // load side: iteration cursor (pass lit, stage lst) ; store side: (pass sit, stage sst) + TMEM stage ring (s, ph)
-    int lit = 0, lst = 0, lj = 0;
+    int lit = 0, lst = 0;
     uint32_t l_idx_tile = 0;
     bool l_absent = false;
-    auto issue = [&](uint4 (&v)[2][2][2]) -> bool {
+    auto issue = [&](uint2 (&v)[2][4][2]) -> bool {      // [16-lane half h][repeat g][row, row + 8]
       if (lst == 0) {                                 // first stage of a pass: its index tile must have landed
         const int n = (lit << lT) + t;
         const int buf = n & (NI - 1);
-        l_absent = t == 1 && (int)blockIdx.x + lit * (int)gridDim.x >= nfull;
+        l_absent = t == 1 && absent_of(lit);
         l_idx_tile = idx_base + (uint32_t)buf * idx_buf_bytes;
         mbar_wait_sleep(bars + kBarIdx + 8 * buf, (uint32_t)(n >> lNI) & 1u);
       }
@@ -271,39 +291,44 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       if (have) {
         const uint32_t idx_c = l_idx_tile + row_off +
                                (uint32_t)(CIN <= 64 ? c * Cfg::kOffPerChunk : c / Cfg::kChunksPerOff) * kBM * 4;
-        const int ehalf = CIN > 64 ? (c % Cfg::kChunksPerOff) * 64 : 0;
-        const __nv_bfloat16* src0 = in + ehalf + eo0;
-        const __nv_bfloat16* src1 = in + ehalf + eo1;
+        const __nv_bfloat16* src = in + (CIN > 64 ? (c % Cfg::kChunksPerOff) * 64 : 0);
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
           for (int rr = 0; rr < 2; ++rr) {
-            int rw0, rw1;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw0) : "r"(idx_c + (uint32_t)(slot0 * kBM + h * 16 + rr * 8) * 4) : "memory");
-            if (CIN <= 32) {
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw1) : "r"(idx_c + (uint32_t)(slot1 * kBM + h * 16 + rr * 8) * 4) : "memory");
-            } else {
-              rw1 = rw0;
+            constexpr int kSlots = CIN <= 64 ? 64 / CIN : 1;      // kernel offsets inside the chunk
+            int rw[kSlots];
+#pragma unroll
+            for (int sl = 0; sl < kSlots; ++sl)
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw[sl]) : "r"(idx_c + (uint32_t)(sl * kBM + h * 16 + rr * 8) * 4) : "memory");
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int sl = CIN <= 64 ? (16 * g) / CIN : 0;      // element 16g + 4j of the chunk row
+              const int eo = CIN <= 64 ? (16 * g) % CIN : 16 * g;
+              v[h][g][rr] = make_uint2(0u, 0u);
+              if (rw[sl] >= 0) v[h][g][rr] = __ldg(reinterpret_cast<const uint2*>(src + (size_t)(uint32_t)rw[sl] * CIN + eo));
             }
-            v[h][rr][0] = make_uint4(0u, 0u, 0u, 0u);
-            v[h][rr][1] = make_uint4(0u, 0u, 0u, 0u);
-            if (rw0 >= 0) v[h][rr][0] = __ldg(reinterpret_cast<const uint4*>(src0 + (size_t)(uint32_t)rw0 * CIN));
-            if (rw1 >= 0) v[h][rr][1] = __ldg(reinterpret_cast<const uint4*>(src1 + (size_t)(uint32_t)rw1 * CIN));
           }
       }
-      ++lj;
       if (++lst == nst) { lst = 0; ++lit; }
       return have;
     };
-    int s = 0, sit = 0, sst = 0;
+    int s = 0, sst = 0, free_buf = 0;
     uint32_t ph = 0;
-    auto store = [&](const uint4 (&v)[2][2][2], bool have) {
+    auto store = [&](const uint2 (&v)[2][4][2], bool have) {
       mbar_wait_sleep(bars + kBarEmpty + 8 * s, ph ^ 1u);
       if (have) {
         tc_fence_after();
         const uint32_t ta = ta0 + (uint32_t)(s * 128);
-        tmem_st_16x256b_x4(ta, v[0][0][0], v[0][1][0], v[0][0][1], v[0][1][1]);
-        tmem_st_16x256b_x4(ta + (16u << 16), v[1][0][0], v[1][1][0], v[1][0][1], v[1][1][1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          asm volatile(
+              "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+                  ta + ((uint32_t)(h * 16) << 16)),
+              "r"(v[h][0][0].x), "r"(v[h][0][0].y), "r"(v[h][0][1].x), "r"(v[h][0][1].y), "r"(v[h][1][0].x), "r"(v[h][1][0].y),
+              "r"(v[h][1][1].x), "r"(v[h][1][1].y), "r"(v[h][2][0].x), "r"(v[h][2][0].y), "r"(v[h][2][1].x), "r"(v[h][2][1].y),
+              "r"(v[h][3][0].x), "r"(v[h][3][0].y), "r"(v[h][3][1].x), "r"(v[h][3][1].y)
+              : "memory");
         tmem_st_wait();
         tc_fence_before();
       }
@@ -311,20 +336,22 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       if (++s == NS) { s = 0; ph ^= 1u; }
       if (++sst == nst) {                             // all index reads of this pass were issued one iteration ago
         __syncwarp();
-        if (lane == 0)
-          for (int tt = 0; tt < T; ++tt) mbar_arrive(bars + kBarIdxFree + 8 * (((sit << lT) + tt) & (NI - 1)));
+        if (lane == 0) {
+          mbar_arrive(bars + kBarIdxFree + 8 * free_buf);
+          mbar_arrive(bars + kBarIdxFree + 8 * (free_buf + 1));
+        }
+        free_buf = (free_buf + 2) & (NI - 1);
         sst = 0;
-        ++sit;
       }
     };
-    uint4 va[2][2][2], vb[2][2][2];
+    uint2 va[2][4][2], vb[2][4][2];
     bool ha = false, hb = false;
     if (total > 0) ha = issue(va);
     for (int jj = 0; jj < total; jj += 2) {
-      if (lj < total) hb = issue(vb);
+      if (jj + 1 < total) hb = issue(vb);
       store(va, ha);
       if (jj + 1 >= total) break;
-      if (lj < total) ha = issue(va);
+      if (jj + 2 < total) ha = issue(va);
       store(vb, hb);
     }
   } else if (warp < kGatherWarps) {
@@ -353,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       // per pass: this warp's tile, its index buffer (waited for once), whether the tile exists
       const int n = (it << lT) + t;                    // tile sequence number of this CTA
       const int buf = n & (NI - 1);
-      const bool absent = t == 1 && (int)blockIdx.x + it * (int)gridDim.x >= nfull;
+      const bool absent = t == 1 && absent_of(it);
       const uint32_t idx_tile = idx_base + (uint32_t)buf * idx_buf_bytes;
       mbar_wait_sleep(bars + kBarIdx + 8 * buf, (uint32_t)(n >> lNI) & 1u);   // also for an absent tile: its fill must have landed before the buffer is handed back
       for (int st = 0; st < nst; ++st, ++gst) {
@@ -519,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
         const int bs2 = bs + 1 == NB ? 0 : bs + 1;
         const uint32_t bph2 = bs + 1 == NB ? bph ^ 1u : bph;
         const bool last_st = st == nst - 1;
-        const bool absent = my_t == 1 && (int)blockIdx.x + it * (int)gridDim.x >= nfull;   // single-tile pass
+        const bool absent = my_t == 1 && absent_of(it);   // single-tile pass
         const uint32_t tmem_d = tmem_base + (uint32_t)((n & (ND - 1)) * COUT);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -616,14 +643,14 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
 // K-major SWIZZLE_128B layout the B descriptor expects.
 template <int CIN>
 __global__ void __launch_bounds__(256) ts_pack_kernel(const float* __restrict__ w, int Cout, int K, int Cin_real,
-                                                       int nchunks, __nv_bfloat16* __restrict__ out) {
+                                                       int nchunks, int natural, __nv_bfloat16* __restrict__ out) {
   const long long total = (long long)nchunks * Cout * kChunkK;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int kappa = (int)(i % kChunkK);
     const int n = (int)((i / kChunkK) % Cout);
     const int c = (int)(i / ((long long)kChunkK * Cout));
     const int half = kappa >> 5, wq = (kappa >> 4) & 1, j = (kappa >> 2) & 3, wl = kappa & 3;
-    const int e = 8 * (4 * half + j) + 4 * wq + wl;        // source element of the chunk row
+    const int e = natural ? kappa : 8 * (4 * half + j) + 4 * wq + wl;        // source element of the chunk row
     int k, ci;
     if constexpr (CIN <= 64) {
       k = c * (64 / CIN) + e / CIN;
@@ -640,34 +667,52 @@ __global__ void __launch_bounds__(256) ts_pack_kernel(const float* __restrict__ 
   }
 }
 
-static bool ts_pipe() {
+static int ts_pipe() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("COMB_TS_PIPE");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = e ? atoi(e) : 0;      // 0 (default): r1 loop; 1: pipelined gather; 2: r1 loop with the pipelined variant's register budget
   }
-  return v == 1;
+  return v;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 template <int CIN, int COUT>
-int launch_ts(const ConvFwdArgs& p, cudaStream_t stream) {
+int launch_ts(const ConvFwdArgs& p_in, cudaStream_t stream) {
   using Cfg = TsCfg<CIN, COUT>;
-  const size_t smem = Cfg::smem_bytes(p.K);
+  ConvFwdArgs p = p_in;
+  // Shared-memory rings.  Whatever the kernel does not take stays L1 cache, and the gather lives on L1 hits, so the
+  // rings are not made as deep as the 227 KB allow: COMB_TS_NI index-tile buffers (8 or 4; default 4) and at most
+  // COMB_TS_NB streamed-weight stages (default 4).
+  static const int ni_env = env_int("COMB_TS_NI", 4), nb_env = env_int("COMB_TS_NB", 4), blocked_env = env_int("COMB_TS_BLOCKED", 0);
+  p.blocked = blocked_env;
+  p.ni = (ni_env == 8 && Cfg::n_idx(p.K) == 8) ? 8 : 4;
+  const int idx_bytes = p.ni * Cfg::k_pad(p.K) * kBM * 4;
+  const bool bres = Cfg::b_resident(p.K);
+  int nb = bres ? 0 : (kSmemBudget - 2048 - idx_bytes) / (2 * Cfg::kBBytes);
+  if (nb > kMaxBStages) nb = kMaxBStages;
+  if (!bres && nb > nb_env && nb_env >= 2) nb = nb_env;
+  p.nb = nb;
+  const size_t smem = 2048 + (size_t)idx_bytes + (bres ? (size_t)Cfg::num_chunks(p.K) * Cfg::kBBytes : (size_t)nb * 2 * Cfg::kBBytes);
   static thread_local DevOnce configured;   // per device: the attribute is a per-device property
   if (configured.first()) {
-    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
   }
-  if (smem > 227 * 1024 - 1024 || (!Cfg::b_resident(p.K) && Cfg::b_stages(p.K) < 2)) {
+  if (smem > 227 * 1024 - 1024 || (!bres && nb < 2)) {
     set_error("comb_spconv_fwd_bf16: shared memory %zu exceeds the per-CTA limit", smem);
     return COMB_EINVAL;
   }
   const int nsuper = cdiv(cdiv(p.no_max, kBM), Cfg::tiles_per_pass(p.K));
   const int grid = nsuper < sm_count() ? nsuper : sm_count();
-  if (p.dbg != nullptr) spconv_ts_kernel<CIN, COUT, true, false><<<grid, kThreads, smem, stream>>>(p);   // pipeline trace build
-  else if (ts_pipe()) spconv_ts_kernel<CIN, COUT, false, true><<<grid, kThreads, smem, stream>>>(p);
-  else spconv_ts_kernel<CIN, COUT, false, false><<<grid, kThreads, smem, stream>>>(p);
+  if (p.dbg != nullptr) spconv_ts_kernel<CIN, COUT, true, 0><<<grid, kThreads, smem, stream>>>(p);   // pipeline trace build
+  else if (ts_pipe() == 1) spconv_ts_kernel<CIN, COUT, false, 1><<<grid, kThreads, smem, stream>>>(p);
+  else spconv_ts_kernel<CIN, COUT, false, 0><<<grid, kThreads, smem, stream>>>(p);
   COMB_LAUNCH_CHECK();
   return COMB_OK;
 }
@@ -703,11 +748,12 @@ int ts_pack_weight(const float* weight, int Cout, int K, int Cin, int Cin_p, int
   const long long total = (long long)nchunks * Cout * kChunkK;
   const int grid = cdiv(total, 256);
   __nv_bfloat16* out = (__nv_bfloat16*)wpacked;
+  const int natural = ts_pipe() == 1 ? 1 : 0;   // the pipelined gather keeps K in its natural order
   switch (Cin_p) {
-    case 16: ts_pack_kernel<16><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, out); break;
-    case 32: ts_pack_kernel<32><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, out); break;
-    case 64: ts_pack_kernel<64><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, out); break;
-    case 128: ts_pack_kernel<128><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, out); break;
+    case 16: ts_pack_kernel<16><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, natural, out); break;
+    case 32: ts_pack_kernel<32><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, natural, out); break;
+    case 64: ts_pack_kernel<64><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, natural, out); break;
+    case 128: ts_pack_kernel<128><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, natural, out); break;
     default: COMB_CHECK_ARG(false, "comb_spconv_pack_weight_bf16: Cin_p %d not in {16,32,64,128}", Cin_p);
   }
   COMB_LAUNCH_CHECK();

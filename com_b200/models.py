@@ -309,6 +309,21 @@ def _fusable(m):
         return False
 
 
+def _fused_mode(m, feats):
+    """"eval": fused tensor-core inference chain; "train": fused training step (com_b200.train); None: module path.
+    Switches: COMB_FUSED=0 / COMB_FUSED_TRAIN=0 keep the module path (every conv / BatchNorm1d / ReLU called one by one,
+    exactly as the reference's forward does)."""
+    if os.environ.get("COMB_FUSED", "1") == "0" or not feats.is_cuda or not _fusable(m):
+        return None
+    if not m.training and not torch.is_grad_enabled():
+        return "eval"
+    if m.training and torch.is_grad_enabled() and os.environ.get("COMB_FUSED_TRAIN", "1") != "0" \
+            and any(p.requires_grad for p in m.parameters()) and all(
+                isinstance(b, nn.BatchNorm1d) and b.training and b.affine for b in m.modules() if isinstance(b, nn.modules.batchnorm._BatchNorm)):
+        return "train"
+    return None
+
+
 def patch_reference_backbone(cls):
     """Give the REFERENCE's own VoxelResBackBone8x class (pcdet/models/backbones_3d/spconv_backbone.py:183-293,
     instantiated by the reference's registry with the spconv drop-in underneath) the fused tensor-core eval path:
@@ -324,10 +339,14 @@ def patch_reference_backbone(cls):
     reference_forward = cls.forward
 
     def forward(self, batch_dict):
-        if (os.environ.get("COMB_FUSED", "1") != "0" and not self.training and not torch.is_grad_enabled()
-                and batch_dict['voxel_features'].is_cuda and _fusable(self)):
+        mode = _fused_mode(self, batch_dict['voxel_features'])
+        if mode is not None:
             feats, coords = batch_dict['voxel_features'], batch_dict['voxel_coords']
-            x1, x2, x3, x4, out = self.forward_fused(feats, coords.int(), batch_dict['batch_size'])
+            if mode == "eval":
+                x1, x2, x3, x4, out = self.forward_fused(feats, coords.int(), batch_dict['batch_size'])
+            else:
+                from . import train
+                x1, x2, x3, x4, out = train.forward_train(self, feats, coords.int().contiguous(), batch_dict['batch_size'])
             batch_dict.update({
                 'encoded_spconv_tensor': out, 'encoded_spconv_tensor_stride': 8,
                 'multi_scale_3d_features': {'x_conv1': x1, 'x_conv2': x2, 'x_conv3': x3, 'x_conv4': x4},
@@ -382,8 +401,12 @@ class VoxelResBackBone8x(FusedBackboneMixin, nn.Module):
     def forward(self, batch_dict):
         feats, coords = batch_dict['voxel_features'], batch_dict['voxel_coords']
         batch_size = batch_dict['batch_size']
-        if self.fused and not self.training and not torch.is_grad_enabled():
+        mode = _fused_mode(self, feats) if self.fused else None
+        if mode == "eval":
             x1, x2, x3, x4, out = self.forward_fused(feats, coords.int(), batch_size)
+        elif mode == "train":
+            from . import train
+            x1, x2, x3, x4, out = train.forward_train(self, feats, coords.int().contiguous(), batch_size)
         else:
             x = SparseConvTensor(features=feats, indices=coords.int(), spatial_shape=self.sparse_shape,
                                  batch_size=batch_size)

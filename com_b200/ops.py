@@ -16,7 +16,7 @@ from ._lib import DT_BF16, DT_F32, EPI_AFFINE, EPI_BIAS, EPI_RELU, EPI_RESIDUAL,
 __all__ = [
     "voxelize", "mean_vfe", "hash_build", "conv_out_coords", "conv_out_shape", "nbrmap_build",
     "nbrmap_transpose", "nbrmap_to_pairs", "spconv_fwd_f32", "spconv_dgrad_f32", "spconv_wgrad_f32", "spconv_wgrad_bf16",
-    "pack_weight_bf16", "spconv_fwd_bf16", "affine_relu", "cast_pad", "dense", "dense_gather", "DenseFunction", "points_in_boxes_mask",
+    "pack_weight_bf16", "spconv_fwd_bf16", "affine_relu", "cast_pad", "bn_train_fwd", "bn_train_bwd", "col_sum", "dense", "dense_gather", "DenseFunction", "points_in_boxes_mask",
     "points_in_any_box", "points_in_boxes_index", "boxes_bev", "nms", "box_trig_host", "box_trig4_host",
 ]
 
@@ -472,6 +472,61 @@ def cast_pad(x, ld, n_dev=None):
     n, C = int(x.shape[0]), int(x.shape[1])
     out = torch.empty((n, int(ld)), dtype=torch.bfloat16, device=x.device)
     check(lib.comb_cast_pad(_p(x), n, _p(n_dev), C, _p(out), int(ld), _stream()), "comb_cast_pad")
+    return out
+
+
+def bn_train_fwd(x, gamma, beta, eps, momentum, running_mean=None, running_var=None, residual=None, relu=True,
+                 n_dev=None, out=None):
+    """BatchNorm1d(train) + residual + ReLU; x fp32 or bf16 rows.  -> (out bf16, save_mean, save_invstd)."""
+    lib = _lib.load()
+    _need(x, x.dtype, "x")
+    _need(residual, torch.bfloat16, "residual")
+    for n_, t_ in (("gamma", gamma), ("beta", beta), ("running_mean", running_mean), ("running_var", running_var)):
+        _need(t_, torch.float32, n_)
+    n, C = int(x.shape[0]), int(x.shape[1])
+    out = torch.empty((n, C), dtype=torch.bfloat16, device=x.device) if out is None else out
+    _need(out, torch.bfloat16, "out")
+    mean = torch.empty((C,), dtype=torch.float32, device=x.device)
+    invstd = torch.empty((C,), dtype=torch.float32, device=x.device)
+    nbytes = lib.comb_bn_workspace_bytes(C)
+    if nbytes == 0:
+        raise RuntimeError("bn_train_fwd: C=%d not in {16,32,64,128}" % C)
+    ws = _ws(nbytes, x.device)
+    with _Scope("bn_train", n=n, n_dev=n_dev, C=C, passes=3 + (residual is not None)):
+        check(lib.comb_bn_train_fwd(_p(x), _dt(x), n, _p(n_dev), C, _p(gamma), _p(beta), float(eps), float(momentum),
+                                    _p(running_mean), _p(running_var), _p(residual), int(bool(relu)), _p(out), _p(mean),
+                                    _p(invstd), _p(ws), nbytes, _stream()), "comb_bn_train_fwd")
+    return out, mean, invstd
+
+
+def bn_train_bwd(dy, act, x, gamma, mean, invstd, relu=True, want_g=False, n_dev=None):
+    """-> (dx bf16, g bf16 or None, dgamma, dbeta)."""
+    lib = _lib.load()
+    _need(dy, torch.bfloat16, "dy")
+    _need(act, torch.bfloat16, "act")
+    _need(x, x.dtype, "x")
+    n, C = int(x.shape[0]), int(x.shape[1])
+    dx = torch.empty_like(dy)
+    g = torch.empty_like(dy) if want_g else None
+    dgamma = torch.empty((C,), dtype=torch.float32, device=x.device)
+    dbeta = torch.empty((C,), dtype=torch.float32, device=x.device)
+    nbytes = lib.comb_bn_workspace_bytes(C)
+    ws = _ws(nbytes, x.device)
+    with _Scope("bn_train", n=n, n_dev=n_dev, C=C, passes=6 + int(relu) * 2 + int(want_g)):
+        check(lib.comb_bn_train_bwd(_p(dy), _p(act), _p(x), _dt(x), n, _p(n_dev), C, _p(gamma), _p(mean), _p(invstd),
+                                    int(bool(relu)), _p(dx), _p(g), _p(dgamma), _p(dbeta), _p(ws), nbytes, _stream()),
+              "comb_bn_train_bwd")
+    return dx, g, dgamma, dbeta
+
+
+def col_sum(x, n_dev=None):
+    lib = _lib.load()
+    _need(x, torch.bfloat16, "x")
+    n, C = int(x.shape[0]), int(x.shape[1])
+    out = torch.empty((C,), dtype=torch.float32, device=x.device)
+    nbytes = lib.comb_bn_workspace_bytes(C)
+    ws = _ws(nbytes, x.device)
+    check(lib.comb_col_sum(_p(x), n, _p(n_dev), C, _p(out), _p(ws), nbytes, _stream()), "comb_col_sum")
     return out
 
 

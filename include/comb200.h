@@ -224,6 +224,32 @@ int comb_cast_pad(const float* x, int n_max, const int* n_dev, int C, void* out_
 int comb_permute_rows(const void* in, const int* row_map, int n_max, const int* n_dev, int row_bytes,
                       int scatter, void* out, void* stream);
 
+/* ---- a9, training form: BatchNorm1d(train) + ReLU + residual over the active rows ------------------------
+ * Replaces the eager chain between two sparse convolutions in train() mode — SparseSequential(conv,
+ * nn.BatchNorm1d(eps=1e-3, momentum=0.01), nn.ReLU()) (pcdet/models/backbones_3d/spconv_backbone.py:21-25) and
+ * SparseBasicBlock.forward's bn -> relu -> conv -> bn -> (+identity) -> relu (:50-66) — for the fused training step.
+ * x (the convolution output) is fp32 or bf16 (x_dtype = COMB_DT_*); residual, out, dy, act, dx, g_out are bf16;
+ * all [n_max, C] row-major, C in {16,32,64,128}; n_dev (device int, may
+ * be NULL) is the live row count.  Statistics are reduced deterministically (per-block partial sums in fp64).
+ *   fwd: batch mean / biased variance over the rows; running_mean/var (may be NULL) updated like torch (momentum,
+ *        unbiased variance); out = relu?(x*gamma*invstd + beta - mean*gamma*invstd (+ residual)); save_mean /
+ *        save_invstd [C] are kept for the backward pass.
+ *   bwd: g = dy * (act > 0) if relu else dy (act = the forward's out); dgamma = sum g*xhat, dbeta = sum g,
+ *        dx = gamma*invstd*(g - dbeta/n - xhat*dgamma/n); g_out (may be NULL) receives g, the gradient of the
+ *        residual branch.
+ * comb_col_sum: sum[c] = sum over rows of x[:, c] (bias gradient of a convolution).
+ * workspace: comb_bn_workspace_bytes(C). */
+size_t comb_bn_workspace_bytes(int C);
+int comb_bn_train_fwd(const void* x, int x_dtype, int n_max, const int* n_dev, int C, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var, const void* residual,
+                      int relu, void* out, float* save_mean, float* save_invstd, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int comb_bn_train_bwd(const void* dy, const void* act, const void* x, int x_dtype, int n_max, const int* n_dev, int C,
+                      const float* gamma, const float* save_mean, const float* save_invstd, int relu, void* dx,
+                      void* g_out, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
+int comb_col_sum(const void* x, int n_max, const int* n_dev, int C, float* sum, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
 /* ---- a10: HeightCompression / SparseConvTensor.dense() ---------------------------------------
  * Replaces encoded_spconv_tensor.dense() (pcdet/models/backbones_2d/map_to_bev/
  * height_compression.py:21): out[b, c, z, y, x] = feats[row, c], zero elsewhere; out is fp32
