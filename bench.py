@@ -87,7 +87,7 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
 
     def _run_nvml(self):
-        """fast path: NVML through nvidia_ml_py (a sample every ~5 ms instead of one nvidia-smi process per 0.2-1 s)"""
+        """fast path: NVML through nvidia_ml_py (a sample every ~10 ms instead of one nvidia-smi process per 0.2-1 s)"""
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
@@ -100,7 +100,7 @@ class ClockSampler(threading.Thread):
             r = int(get_reasons(h))
             self.rows.append([str(sm), str(mx)] + [("Active" if r & bits[n] else "Not Active") for n in
                                                    ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
-            self._stop_evt.wait(0.005)
+            self._stop_evt.wait(0.01)
 
     def run(self):
         try:
@@ -317,6 +317,30 @@ def box_ops_leg(torch, frame, peaks):
            "bev_iou": {"ms": ms_iou, "pairs_per_us": nb * nb / ms_iou / 1e3, "achieved_gbs": by_iou / ms_iou / 1e6,
                        "bound": "SFU / latency (1 MB output)"},
            "nms": {"ms": ms_nms, "bound": "latency (mask + one-warp sweep on the device, no host round trip)"}}
+    # e2e: the same operations through the reference-facing API with HOST buffers (numpy / CPU tensors in, result back
+    # on the host: what a DataBaseSampler worker or CenterHead post-processing actually waits for), wall clock
+    from com_b200.pcdet_ops import box_ops
+
+    def wall(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return 1e3 * (time.perf_counter() - t0) / reps
+
+    scores = torch.linspace(1.0, 0.0, nb, device=dev)
+    out["e2e"] = {
+        "api": "com_b200.pcdet_ops.box_ops (signatures of iou3d_nms_utils.py / roiaware_pool3d_utils.py / box_utils.py), "
+               "host buffers in and out, wall clock per call",
+        "points_in_boxes_cpu_ms": wall(lambda: box_ops.points_in_boxes_cpu(pts_np, boxes_np), reps=3),
+        "points_in_boxes_cpu_d2h_bytes": nb * P * 4,
+        "boxes_bev_iou_cpu_ms": wall(lambda: box_ops.boxes_bev_iou_cpu(cl_np, cl_np)),
+        "boxes_bev_iou_cpu_d2h_bytes": nb * nb * 4,
+        "nms_gpu_ms": wall(lambda: box_ops.nms_gpu(cl, scores, 0.7)[0].cpu()),
+        "note": "points_in_boxes_cpu must hand back the reference's (Nb,P) int32 mask: %.0f MB of device->host copy into "
+                "pageable memory dominate the %.3f ms kernel" % (nb * P * 4 / 1e6, ms_pib)}
     # reference CPU path beside it
     kind = "port"
     try:
@@ -385,13 +409,39 @@ def comaug_leg(torch, frame, peaks):
     ms_small = timed(lambda: ops.boxes_bev(cand, exist, flavour="cpu", what="iou", trig_a=tc, trig_b=te, out=o_small))
     ms_full = timed(lambda: ops.boxes_bev(cand, cand, flavour="cpu", what="iou", trig_a=tc, trig_b=tc, out=o_full))
     ms_rm = timed(lambda: ops.points_in_boxes_mask(pts, rm, trm, out=mask))
+    any_ = torch.empty((int(pts.shape[0]),), dtype=torch.uint8, device=dev)
+    ms_any = timed(lambda: ops.points_in_any_box(pts, rm, trm, out=any_))
     by_full = 2 * 10000 * 28.0 + 1e8 * 4.0
     out = {"workload": "configs[3]: rotated BEV IoU 10000 x 100 and 10000 x 10000 (400 MB out), points_in_boxes of 35 boxes "
                        "on %d points" % pts.shape[0],
            "iou_10k_x_100_ms": ms_small, "iou_10k_x_10k_ms": ms_full,
            "iou_10k_x_10k": {"achieved_gbs": by_full / ms_full / 1e6, "frac_of_hbm_peak": by_full / ms_full / 1e6 / peaks["hbm"],
                              "pairs_overlapping": int((o_full > 0).sum().item()), "bound": "hbm (IoU matrix write)"},
-           "points_in_boxes_35_ms": ms_rm}
+           "points_in_boxes_35_ms": ms_rm, "points_in_any_box_35_ms": ms_any}
+    # e2e through the reference-facing API with HOST buffers (numpy in, numpy out), wall clock per call: what the
+    # DataBaseSampler sees (database_sampler_v2.py:535-539,600-604)
+    from com_b200.pcdet_ops import box_ops
+    frame_np = np.ascontiguousarray(frame)
+
+    def wall(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return 1e3 * (time.perf_counter() - t0) / reps
+
+    def removal_via_mask():                  # the reference's own body of remove_points_in_boxes3d (box_utils.py:128-129)
+        m = box_ops.points_in_boxes_cpu(frame_np[:, 0:3], rm_np)
+        return frame_np[m.sum(axis=0) == 0]
+
+    out["e2e"] = {
+        "api": "com_b200.pcdet_ops.box_ops, host buffers in and out, wall clock per call",
+        "boxes_bev_iou_cpu_10k_x_100_ms": wall(lambda: box_ops.boxes_bev_iou_cpu(cand_np, exist_np)),
+        "remove_points_in_boxes3d_35_ms": wall(lambda: box_ops.remove_points_in_boxes3d(frame_np, rm_np)),
+        "remove_points_in_boxes3d_35_via_full_mask_ms": wall(removal_via_mask),
+        "remove_points_d2h_bytes": {"any_box_kernel": int(pts.shape[0]), "full_mask": 35 * int(pts.shape[0]) * 4}}
     kind = "port"
     try:
         if build_ref.available():
@@ -506,25 +556,30 @@ def train_leg(torch, frames, world=1, local_rank=0):
         cap = _Capture()
         sparse.config.compute, sparse.config.wgrad = "bf16", "bf16"
         net.fused = True                    # the wgrad launches of the fused step (key-ordered rows)
+        from com_b200 import train as ctrain
+        tr = ctrain.get_trainer(net)
+        graph_mode, tr.use_graph = tr.use_graph, False     # the hook sees launches only when they are made one by one
         ops.set_profiler(cap)
         try:
             step()
         finally:
             ops.set_profiler(None)
+            tr.use_graph = graph_mode
         torch.cuda.synchronize()
         evs = []
         torch.cuda._sleep(int(6e6))
         for c in cap.calls:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ops.spconv_wgrad_bf16(c["feats"], c["dout"], c["nbr"], c["cin_real"])
+            ops.spconv_wgrad_bf16(c["feats"], c["dout"], c["nbr"], c["cin_real"], no_dev=c.get("no_dev"))
             e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
         layers, tot_ms, tot_fl = {}, 0.0, 0.0
         for c, (e0, e1) in zip(cap.calls, evs):
             ms = e0.elapsed_time(e1)
-            fl = 2.0 * float((c["nbr"] >= 0).sum().item()) * c["cin"] * c["cout"]
+            live = int(c["no_dev"].item()) if c.get("no_dev") is not None else int(c["nbr"].shape[1])
+            fl = 2.0 * float((c["nbr"][:, :live] >= 0).sum().item()) * c["cin"] * c["cout"]
             key = "%dx%d_K%d" % (c["cin"], c["cout"], c["K"])
             a = layers.setdefault(key, {"n": 0, "ms": 0.0, "flops": 0.0})
             a["n"] += 1
@@ -601,6 +656,8 @@ def ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # before any pinned allocation: run (and first-touch the staging buffers) on the GPU's own NUMA node
+    numa = cdist.bind_to_gpu_numa(local_rank)
     lib = _lib.load(build_if_missing=False)
     peaks = load_peaks()
 
@@ -782,8 +839,8 @@ def ours(args):
         rows_seen.add(stream.result(prev)["rows"])       # the caller owns the last result: every D2H has landed
         e_last = torch.cuda.Event(enable_timing=True)
         for tk in range(max(0, stream.k - stream.LANES), stream.k):
-            stream.s_out.wait_event(stream.done_event(tk))
-        e_last.record(stream.s_out)
+            stream.s_pay.wait_event(stream.done_event(tk))
+        e_last.record(stream.s_pay)
         torch.cuda.synchronize()
         t_wall = time.perf_counter() - t_wall0
         t_e2e = e0.elapsed_time(e_last) / 1e3
@@ -860,8 +917,9 @@ def ours(args):
                         n_ring, n_ring * host.numel() * 4 / 1e6),
                     "api": "FrameStream.submit/result (two lanes = two step graphs in flight; H2D, kernels and D2H of "
                            "neighbouring steps overlap)",
-                    "result": "encoded_spconv_tensor (features bf16 + indices, capacity-sized) + all row counts to pinned "
-                              "host; the dense BEV tensor is produced on the device"},
+                    "result": "all row counts, then exactly the live rows of encoded_spconv_tensor (features bf16 + "
+                              "indices) to pinned host; the dense BEV tensor is produced on the device",
+                    "numa": numa},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "breakdown_ms_per_step": {k: v["ms"] / args.steps for k, v in fam.items()},
             "profiled_ms_per_step": 1e3 * t_prof / args.steps,       # sum of the per-family device times (single stream)

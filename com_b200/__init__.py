@@ -41,9 +41,33 @@ def _hook_box_utils(mod):
     mod.remove_points_in_boxes3d = remove_points_in_boxes3d
 
 
+def _hook_center_head(mod):
+    """pcdet/models/dense_heads/center_head.py:266-317 (and the COM head in curriculum_center_head.py): post-processing
+    through comb_centerhead_decode_nms when the configuration is covered, the reference method otherwise."""
+    from .pcdet_ops import center_decode
+    for name in ("CenterHead", "CurriculumCenterHead"):
+        cls = getattr(mod, name, None)
+        if cls is None or getattr(cls.generate_predicted_boxes, "_comb", False):
+            continue
+        reference_method = cls.generate_predicted_boxes
+
+        def generate_predicted_boxes(self, batch_size, pred_dicts, _ref=reference_method):
+            import os
+            if os.environ.get("COMB_FUSED_DECODE", "1") != "0" and center_decode.supported(self) \
+                    and pred_dicts[0]["hm"].is_cuda:
+                return center_decode.generate_predicted_boxes(self, batch_size, pred_dicts)
+            return _ref(self, batch_size, pred_dicts)
+
+        generate_predicted_boxes._comb = True
+        generate_predicted_boxes.reference = reference_method
+        cls.generate_predicted_boxes = generate_predicted_boxes
+
+
 POST_IMPORT_HOOKS = {
     "pcdet.models.backbones_3d.spconv_backbone": _hook_spconv_backbone,
     "pcdet.utils.box_utils": _hook_box_utils,
+    "pcdet.models.dense_heads.center_head": _hook_center_head,
+    "pcdet.models.dense_heads.curriculum_center_head": _hook_center_head,
 }
 
 

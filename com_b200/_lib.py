@@ -76,6 +76,11 @@ SIGNATURES = {
     "comb_boxes_bev": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P]),
     "comb_nms_workspace_bytes": (c_size_t, [c_int]),
     "comb_nms": (c_int, [_P, _P, c_int, c_float, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "comb_nms_dev": (c_int, [_P, _P, c_int, _P, c_float, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "comb_centerhead_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "comb_centerhead_decode_nms": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
+                                           c_float, c_float, _PF, c_float, _P, c_float, c_int, c_int, _P, _P, _P, _P, _P,
+                                           c_size_t, _P]),
 }
 
 

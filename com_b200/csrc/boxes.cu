@@ -305,8 +305,9 @@ __device__ __forceinline__ float iou_axis_aligned(const float* a, const float* b
 // 64 blocks x 64 threads and ~0.25 ms.)
 template <bool CPUF, bool ROT>
 __global__ void __launch_bounds__(256) nms_mask_kernel(const float* __restrict__ boxes, const float* __restrict__ trig,
-                                                        int n, float thresh, unsigned long long* __restrict__ mask,
-                                                        int col_blocks) {
+                                                        int n_max, const int* __restrict__ n_dev, float thresh,
+                                                        unsigned long long* __restrict__ mask, int col_blocks) {
+  const int n = eff_n(n_max, n_dev);
   const int cb = blockIdx.x, r0 = blockIdx.y * 4;
   if (cb < (r0 >> 6)) return;                       // whole block left of the diagonal (4 | 64: one row block per block)
   __shared__ BoxRec scol[64], srow[4];
@@ -339,10 +340,11 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(const float* __restrict__
 }
 
 // Greedy sweep (iou3d_nms.cpp:121-133) on the device: one warp, suppression words in shared memory.
-__global__ void __launch_bounds__(32) nms_sweep_kernel(const unsigned long long* __restrict__ mask, int n,
-                                                        int col_blocks, long long* __restrict__ keep,
-                                                        int* __restrict__ num_keep) {
+__global__ void __launch_bounds__(32) nms_sweep_kernel(const unsigned long long* __restrict__ mask, int n_max,
+                                                        const int* __restrict__ n_dev, int col_blocks,
+                                                        long long* __restrict__ keep, int* __restrict__ num_keep) {
   extern __shared__ unsigned long long remv[];
+  const int n = eff_n(n_max, n_dev);
   const int lane = threadIdx.x;
   for (int j = lane; j < col_blocks; j += 32) remv[j] = 0ull;
   __syncwarp();
@@ -364,10 +366,11 @@ __global__ void __launch_bounds__(32) nms_sweep_kernel(const unsigned long long*
 // Same sweep with the whole suppression matrix staged in shared memory first (n * col_blocks * 8 bytes <= ~200 KB, i.e.
 // n <= ~1200: the CenterHead case of <= 500 boxes per frame is 32 KB).  The global-memory form above pays one
 // dependent L2 round trip per KEPT box (r1: 0.36 ms for 500 boxes at thresh 0.7, almost all of it the sweep).
-__global__ void __launch_bounds__(256) nms_sweep_smem_kernel(const unsigned long long* __restrict__ mask, int n,
-                                                              int col_blocks, long long* __restrict__ keep,
-                                                              int* __restrict__ num_keep) {
+__global__ void __launch_bounds__(256) nms_sweep_smem_kernel(const unsigned long long* __restrict__ mask, int n_max,
+                                                              const int* __restrict__ n_dev, int col_blocks,
+                                                              long long* __restrict__ keep, int* __restrict__ num_keep) {
   extern __shared__ unsigned long long sm[];      // [col_blocks] removed bits, then [n][col_blocks] matrix
+  const int n = eff_n(n_max, n_dev);
   unsigned long long* remv = sm;
   unsigned long long* rows = sm + col_blocks;
   const int total = n * col_blocks;
@@ -657,8 +660,9 @@ extern "C" size_t comb_nms_workspace_bytes(int n) {
   return align_up((size_t)n * cb * 8, 256);
 }
 
-extern "C" int comb_nms(const float* boxes, const float* trig, int n, float thresh, int rotated, int flavour,
-                        long long* keep, int* num_keep, void* workspace, size_t workspace_bytes, void* stream_) {
+extern "C" int comb_nms_dev(const float* boxes, const float* trig, int n, const int* n_dev, float thresh, int rotated,
+                            int flavour, long long* keep, int* num_keep, void* workspace, size_t workspace_bytes,
+                            void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   COMB_CHECK_ARG(n >= 0 && keep && num_keep, "comb_nms: bad arguments");
   COMB_CHECK_ARG(flavour == 0 || flavour == 1, "comb_nms: flavour must be 0 (cpu) or 1 (gpu)");
@@ -674,11 +678,11 @@ extern "C" int comb_nms(const float* boxes, const float* trig, int n, float thre
   dim3 grid(cb, cdiv(n, 4));       // 4 rows x 64 columns per block
   COMB_CHECK_ARG(grid.y <= 65535, "comb_nms: too many boxes (%d)", n);
   if (!rotated)
-    nms_mask_kernel<false, false><<<grid, 256, 0, stream>>>(boxes, trig, n, thresh, mask, cb);
+    nms_mask_kernel<false, false><<<grid, 256, 0, stream>>>(boxes, trig, n, n_dev, thresh, mask, cb);
   else if (flavour == 0)
-    nms_mask_kernel<true, true><<<grid, 256, 0, stream>>>(boxes, trig, n, thresh, mask, cb);
+    nms_mask_kernel<true, true><<<grid, 256, 0, stream>>>(boxes, trig, n, n_dev, thresh, mask, cb);
   else
-    nms_mask_kernel<false, true><<<grid, 256, 0, stream>>>(boxes, trig, n, thresh, mask, cb);
+    nms_mask_kernel<false, true><<<grid, 256, 0, stream>>>(boxes, trig, n, n_dev, thresh, mask, cb);
   COMB_LAUNCH_CHECK();
   const size_t staged = ((size_t)n * cb + cb) * 8;
   if (staged <= 200 * 1024) {
@@ -686,10 +690,15 @@ extern "C" int comb_nms(const float* boxes, const float* trig, int n, float thre
     if (configured.first()) {
       COMB_CUDA(cudaFuncSetAttribute(nms_sweep_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
-    nms_sweep_smem_kernel<<<1, 256, staged, stream>>>(mask, n, cb, keep, num_keep);
+    nms_sweep_smem_kernel<<<1, 256, staged, stream>>>(mask, n, n_dev, cb, keep, num_keep);
   } else {
-    nms_sweep_kernel<<<1, 32, (size_t)cb * 8, stream>>>(mask, n, cb, keep, num_keep);
+    nms_sweep_kernel<<<1, 32, (size_t)cb * 8, stream>>>(mask, n, n_dev, cb, keep, num_keep);
   }
   COMB_LAUNCH_CHECK();
   return COMB_OK;
+}
+
+extern "C" int comb_nms(const float* boxes, const float* trig, int n, float thresh, int rotated, int flavour,
+                        long long* keep, int* num_keep, void* workspace, size_t workspace_bytes, void* stream_) {
+  return comb_nms_dev(boxes, trig, n, nullptr, thresh, rotated, flavour, keep, num_keep, workspace, workspace_bytes, stream_);
 }

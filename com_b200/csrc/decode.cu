@@ -1,0 +1,288 @@
+// f2 — CenterHead post-processing on the device: heat-map top-K -> gather -> box decode -> range / score mask -> rotated
+// NMS, one launch sequence per batch and no host round trip.
+//
+// Replaces the eager chain of the reference
+//   CenterHead.generate_predicted_boxes          pcdet/models/dense_heads/center_head.py:266-317
+//   centernet_utils.decode_bbox_from_heatmap     pcdet/models/model_utils/centernet_utils.py:199-279 (_topk :180-196)
+//   model_nms_utils.class_agnostic_nms           pcdet/models/model_utils/model_nms_utils.py:6-25
+// (two torch.topk, ~25 gather / elementwise launches, boolean-mask indexing with a host synchronisation per frame, a
+// second topk, the NMS with its blocking copies).
+//
+// _topk takes the K best of every class and then the K best of those C*K: that is the global top-K over (class, y, x),
+// sorted by score.  sigmoid is monotone, so the selection runs on the LOGITS: a 3-level radix select (11 + 11 + 10 bits
+// of the order-preserving integer image of the float) finds the K-th largest key exactly, ties are broken towards the
+// smaller flat index, the K winners are bitonic-sorted in shared memory.  Decode arithmetic follows the reference
+// operation by operation with separately rounded fp32 multiplies and adds (torch runs them as separate kernels).
+#include "common.cuh"
+
+namespace comb {
+namespace {
+
+constexpr int kDecThreads = 1024;
+constexpr int kDecMaxK = 1024;
+
+__device__ __forceinline__ unsigned order_key(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+struct DecodeArgs {
+  const float *hm, *center, *center_z, *dim, *rot;
+  int B, C, H, W, K;
+  float stride, vx, vy, rx, ry;
+  float lim[6];
+  float score_thresh;
+  const int* label_map;
+  float* boxes;      // [B][K][7]   masked candidates, score-sorted, compacted
+  float* scores;     // [B][K]
+  int* labels;       // [B][K]
+  int* counts;       // [B]
+};
+
+// one block per frame
+__global__ void __launch_bounds__(kDecThreads) centerhead_topk_decode_kernel(DecodeArgs a) {
+  __shared__ unsigned hist[2048];
+  __shared__ unsigned warp_tot[32];
+  __shared__ unsigned long long cand[kDecMaxK];     // (key << 32) | (0xFFFFFFFF - index): larger = better
+  __shared__ unsigned eq_idx[kDecMaxK];
+  __shared__ unsigned s_prefix, s_remaining, s_cnt_gt, s_cnt_eq;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int HW = a.H * a.W, N = a.C * HW;
+  const float* hm = a.hm + (size_t)b * N;
+  const int K = a.K < N ? a.K : N;
+
+  // ---- radix select of the K-th largest key
+  if (tid == 0) { s_prefix = 0u; s_remaining = (unsigned)K; }
+  unsigned pmask = 0u;
+  const int shifts[3] = {21, 10, 0}, nbits[3] = {11, 11, 10};
+  for (int lvl = 0; lvl < 3; ++lvl) {
+    const int shift = shifts[lvl], nb = 1 << nbits[lvl];
+    for (int i = tid; i < 2048; i += kDecThreads) hist[i] = 0u;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    for (int i = tid; i < N; i += kDecThreads) {
+      const unsigned key = order_key(__ldg(hm + i));
+      if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & (nb - 1)], 1u);
+    }
+    __syncthreads();
+    // suffix sums over the bins (thread t owns bins 2t, 2t+1 counted from the TOP)
+    const unsigned remaining = s_remaining;
+    const int b0 = nb - 1 - 2 * tid, b1 = b0 - 1;
+    const unsigned h0 = b0 >= 0 ? hist[b0] : 0u, h1 = b1 >= 0 ? hist[b1] : 0u;
+    unsigned v = h0 + h1, incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = warp_tot[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned n = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += n;
+      }
+      warp_tot[lane] = wi - w;                      // exclusive
+    }
+    __syncthreads();
+    const unsigned above = warp_tot[warp] + incl - v;          // elements in bins above b0
+    // the bin where the running count from the top first reaches `remaining`
+    if (b0 >= 0 && above < remaining && above + h0 >= remaining) {
+      s_prefix = prefix | ((unsigned)b0 << shift);
+      s_remaining = remaining - above;
+    } else if (b1 >= 0 && above + h0 < remaining && above + h0 + h1 >= remaining) {
+      s_prefix = prefix | ((unsigned)b1 << shift);
+      s_remaining = remaining - above - h0;
+    }
+    pmask |= (unsigned)(nb - 1) << shift;
+    __syncthreads();
+  }
+  const unsigned kth = s_prefix;                    // exact key of the K-th largest element
+  const unsigned need_eq = s_remaining;             // how many elements equal to it belong to the top K
+
+  // ---- collect: everything above the K-th key, and the ties at the K-th key (smallest indices first)
+  if (tid == 0) { s_cnt_gt = 0u; s_cnt_eq = 0u; }
+  __syncthreads();
+  for (int i = tid; i < N; i += kDecThreads) {
+    const unsigned key = order_key(__ldg(hm + i));
+    if (key > kth) {
+      const unsigned s = atomicAdd(&s_cnt_gt, 1u);
+      if (s < (unsigned)kDecMaxK) cand[s] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (unsigned)i);
+    } else if (key == kth) {
+      const unsigned s = atomicAdd(&s_cnt_eq, 1u);
+      if (s < (unsigned)kDecMaxK) eq_idx[s] = (unsigned)i;
+    }
+  }
+  __syncthreads();
+  const unsigned n_gt = s_cnt_gt;
+  unsigned n_eq = s_cnt_eq < (unsigned)kDecMaxK ? s_cnt_eq : (unsigned)kDecMaxK;
+  // ties: the `need_eq` smallest indices (rank by counting: n_eq is tiny unless the heat map is constant)
+  for (unsigned e = tid; e < n_eq; e += kDecThreads) {
+    const unsigned me = eq_idx[e];
+    unsigned rank = 0;
+    for (unsigned o = 0; o < n_eq; ++o) rank += eq_idx[o] < me ? 1u : 0u;
+    if (rank < need_eq && n_gt + rank < (unsigned)kDecMaxK)
+      cand[n_gt + rank] = ((unsigned long long)kth << 32) | (0xFFFFFFFFu - me);
+  }
+  // pad to a power of two for the sort
+  int P = 1;
+  while (P < K) P <<= 1;
+  for (int i = K + tid; i < P; i += kDecThreads) cand[i] = 0ull;
+  __syncthreads();
+  // ---- bitonic sort, descending
+  for (int size = 2; size <= P; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < P; i += kDecThreads) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool desc = (i & size) == 0;
+          const unsigned long long x = cand[i], y = cand[j];
+          if ((x < y) == desc) { cand[i] = y; cand[j] = x; }
+        }
+      }
+      __syncthreads();
+    }
+
+  // ---- decode + mask (thread t = candidate t of the sorted list)
+  bool ok = false;
+  float box[7], score = 0.f;
+  int label = 0;
+  if (tid < K) {
+    const unsigned long long c = cand[tid];
+    const unsigned idx = 0xFFFFFFFFu - (unsigned)(c & 0xFFFFFFFFull);
+    const float logit = key_to_float((unsigned)(c >> 32));
+    score = 1.0f / (1.0f + expf(-logit));                         // torch.sigmoid
+    const int cls = (int)(idx / (unsigned)HW), pos = (int)(idx % (unsigned)HW);
+    const int y = pos / a.W, x = pos % a.W;
+    const size_t f2 = (size_t)b * 2 * HW, f1 = (size_t)b * HW, f3 = (size_t)b * 3 * HW;
+    const float cx = __ldg(a.center + f2 + pos), cy = __ldg(a.center + f2 + HW + pos);
+    const float rc = __ldg(a.rot + f2 + pos), rs = __ldg(a.rot + f2 + HW + pos);
+    // xs = (x + center_x) * feature_map_stride * voxel_size[0] + point_cloud_range[0], every op rounded on its own
+    box[0] = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn((float)x, cx), a.stride), a.vx), a.rx);
+    box[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn((float)y, cy), a.stride), a.vy), a.ry);
+    box[2] = __ldg(a.center_z + f1 + pos);
+    box[3] = expf(__ldg(a.dim + f3 + pos));
+    box[4] = expf(__ldg(a.dim + f3 + HW + pos));
+    box[5] = expf(__ldg(a.dim + f3 + 2 * HW + pos));
+    box[6] = atan2f(rs, rc);
+    ok = box[0] >= a.lim[0] && box[1] >= a.lim[1] && box[2] >= a.lim[2] && box[0] <= a.lim[3] && box[1] <= a.lim[4] &&
+         box[2] <= a.lim[5] && score > a.score_thresh;
+    label = (a.label_map != nullptr ? __ldg(a.label_map + cls) : cls) + 1;
+  }
+  // order-preserving compaction
+  const unsigned bal = __ballot_sync(0xffffffffu, ok);
+  const unsigned before = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) warp_tot[warp] = __popc(bal);
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = warp_tot[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned n = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += n;
+    }
+    warp_tot[lane] = wi - w;
+    if (lane == 31) a.counts[b] = (int)wi;
+  }
+  __syncthreads();
+  if (ok) {
+    const int o = (int)(warp_tot[warp] + before);
+    float* bo = a.boxes + ((size_t)b * a.K + o) * 7;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) bo[q] = box[q];
+    a.scores[(size_t)b * a.K + o] = score;
+    a.labels[(size_t)b * a.K + o] = label;
+  }
+}
+
+// final gather of the kept boxes: out[b][j] = cand[b][keep[b][j]] for j < min(num_keep, post_max)
+__global__ void __launch_bounds__(256) centerhead_gather_keep_kernel(const float* __restrict__ boxes,
+                                                                      const float* __restrict__ scores,
+                                                                      const int* __restrict__ labels,
+                                                                      const long long* __restrict__ keep,
+                                                                      const int* __restrict__ num_keep, int K, int post_max,
+                                                                      float* __restrict__ out_boxes,
+                                                                      float* __restrict__ out_scores,
+                                                                      int* __restrict__ out_labels,
+                                                                      int* __restrict__ out_counts) {
+  const int b = blockIdx.x;
+  int n = num_keep[b];
+  n = n < post_max ? n : post_max;
+  if (threadIdx.x == 0) out_counts[b] = n;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const int src = (int)keep[(size_t)b * K + j];
+    for (int q = 0; q < 7; ++q) out_boxes[((size_t)b * K + j) * 7 + q] = boxes[((size_t)b * K + src) * 7 + q];
+    out_scores[(size_t)b * K + j] = scores[(size_t)b * K + src];
+    out_labels[(size_t)b * K + j] = labels[(size_t)b * K + src];
+  }
+}
+
+}  // namespace
+}  // namespace comb
+
+using namespace comb;
+
+extern "C" size_t comb_nms_workspace_bytes(int n);
+extern "C" int comb_nms_dev(const float* boxes, const float* trig, int n_max, const int* n_dev, float thresh, int rotated,
+                            int flavour, long long* keep, int* num_keep, void* workspace, size_t workspace_bytes,
+                            void* stream_);
+
+extern "C" size_t comb_centerhead_workspace_bytes(int B, int K) {
+  if (B < 1 || K < 1 || K > kDecMaxK) return 0;
+  const size_t per = align_up((size_t)K * 7 * 4, 256) + 2 * align_up((size_t)K * 4, 256) + align_up((size_t)K * 8, 256) +
+                     comb_nms_workspace_bytes(K);
+  return (size_t)B * per + align_up((size_t)2 * B * 4, 256);
+}
+
+extern "C" int comb_centerhead_decode_nms(const float* hm, const float* center, const float* center_z, const float* dim,
+                                          const float* rot, int B, int C, int H, int W, int K, float stride, float vx,
+                                          float vy, float rx, float ry, const float* limit_range, float score_thresh,
+                                          const int* label_map, float nms_thresh, int nms_pre_max, int nms_post_max,
+                                          float* out_boxes, float* out_scores, int* out_labels, int* out_counts,
+                                          void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(B >= 1 && C >= 1 && H >= 1 && W >= 1, "comb_centerhead_decode_nms: bad shape");
+  COMB_CHECK_ARG(K >= 1 && K <= kDecMaxK, "comb_centerhead_decode_nms: K %d outside [1,%d]", K, kDecMaxK);
+  COMB_CHECK_ARG((long long)C * H * W < (1ll << 31), "comb_centerhead_decode_nms: heat map too large");
+  COMB_CHECK_ARG(hm && center && center_z && dim && rot && limit_range, "comb_centerhead_decode_nms: null input");
+  COMB_CHECK_ARG(out_boxes && out_scores && out_labels && out_counts, "comb_centerhead_decode_nms: null output");
+  COMB_CHECK_ARG(workspace && workspace_bytes >= comb_centerhead_workspace_bytes(B, K),
+                 "comb_centerhead_decode_nms: workspace too small");
+  COMB_CHECK_ARG(nms_pre_max >= 1 && nms_post_max >= 1, "comb_centerhead_decode_nms: bad NMS sizes");
+  uint8_t* w = (uint8_t*)workspace;
+  float* c_boxes = (float*)w;        w += (size_t)B * align_up((size_t)K * 7 * 4, 256);
+  float* c_scores = (float*)w;       w += (size_t)B * align_up((size_t)K * 4, 256);
+  int* c_labels = (int*)w;           w += (size_t)B * align_up((size_t)K * 4, 256);
+  long long* keep = (long long*)w;   w += (size_t)B * align_up((size_t)K * 8, 256);
+  int* c_counts = (int*)w;
+  int* num_keep = c_counts + B;      w += align_up((size_t)2 * B * 4, 256);
+  uint8_t* nms_ws = w;
+  // the per-frame strides above are K elements only when K*4 etc. are multiples of 256: use plain K strides instead
+  // (simpler addressing in the kernels) — the workspace formula over-allocates, which is harmless
+  DecodeArgs a;
+  a.hm = hm; a.center = center; a.center_z = center_z; a.dim = dim; a.rot = rot;
+  a.B = B; a.C = C; a.H = H; a.W = W; a.K = K;
+  a.stride = stride; a.vx = vx; a.vy = vy; a.rx = rx; a.ry = ry;
+  for (int i = 0; i < 6; ++i) a.lim[i] = limit_range[i];
+  a.score_thresh = score_thresh;
+  a.label_map = label_map;
+  a.boxes = c_boxes; a.scores = c_scores; a.labels = c_labels; a.counts = c_counts;
+  centerhead_topk_decode_kernel<<<B, kDecThreads, 0, stream>>>(a);
+  COMB_LAUNCH_CHECK();
+  const int n_max = K < nms_pre_max ? K : nms_pre_max;
+  const size_t nms_bytes = comb_nms_workspace_bytes(K);
+  for (int b = 0; b < B; ++b) {
+    int rc = comb_nms_dev(c_boxes + (size_t)b * K * 7, nullptr, n_max, c_counts + b, nms_thresh, 1, 1, keep + (size_t)b * K,
+                          num_keep + b, nms_ws + (size_t)b * nms_bytes, nms_bytes, stream_);
+    if (rc != COMB_OK) return rc;
+  }
+  centerhead_gather_keep_kernel<<<B, 256, 0, stream>>>(c_boxes, c_scores, c_labels, keep, num_keep, K, nms_post_max,
+                                                        out_boxes, out_scores, out_labels, out_counts);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}

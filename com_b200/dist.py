@@ -56,3 +56,74 @@ def sum_over_ranks(value, device=None):
 def barrier():
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+# ---------------------------------------------------------------------------------------------------- NUMA placement
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(index):
+    """NUMA node of GPU `index` from sysfs (None when the platform does not say)."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        if all(hasattr(pr, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = "%04x:%02x:%02x.0" % (int(pr.pci_domain_id), int(pr.pci_bus_id), int(pr.pci_device_id))
+        else:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else str(bus)).lower()
+            if len(bus.split(":")[0]) == 8:              # NVML prints an 8-digit PCI domain, sysfs uses 4
+                bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa(local_rank):
+    """Run this process — and, by first touch, allocate its pinned staging buffers — on the NUMA node the rank's GPU hangs
+    off.  One process per GPU on a two-socket box otherwise lands wherever the launcher was started: r1's 8-GPU run
+    had all ranks on node 0 (`topology`), so the H2D/D2H traffic of GPUs 4-7 (4 x ~20 GB/s) crossed the socket
+    interconnect and end-to-end scaling bent to 0.70 while the device-resident number scaled at 0.99.
+    Best effort: CPU affinity to the node's cores that the cpuset allows, and a preferred-node memory policy
+    (set_mempolicy) so pinned pages come from that node even when the cpuset keeps the threads elsewhere.
+    Call BEFORE allocating pinned memory.  Returns a dict describing what was done (goes into the bench line)."""
+    import ctypes
+    info = {"gpu": int(local_rank), "node": None, "cpus_bound": 0, "mempolicy": False}
+    if os.environ.get("COMB_NUMA_BIND", "1") == "0":
+        info["disabled"] = True
+        return info
+    node = gpu_numa_node(local_rank)
+    info["node"] = node
+    if node is None:
+        return info
+    try:
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            node_cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        want = node_cpus & allowed
+        if want:
+            os.sched_setaffinity(0, want)
+            info["cpus_bound"] = len(want)
+    except Exception as e:
+        info["affinity_error"] = "%s: %s" % (type(e).__name__, e)
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238       # x86_64
+        nbits = 64 * ((node // 64) + 1)
+        mask = (ctypes.c_ulong * (nbits // 64))()
+        mask[node // 64] = 1 << (node % 64)
+        rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), nbits + 1)
+        info["mempolicy"] = rc == 0
+    except Exception as e:
+        info["mempolicy_error"] = "%s: %s" % (type(e).__name__, e)
+    return info

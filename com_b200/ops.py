@@ -17,7 +17,7 @@ __all__ = [
     "voxelize", "mean_vfe", "hash_build", "conv_out_coords", "conv_out_shape", "nbrmap_build",
     "nbrmap_transpose", "nbrmap_to_pairs", "spconv_fwd_f32", "spconv_dgrad_f32", "spconv_wgrad_f32", "spconv_wgrad_bf16",
     "pack_weight_bf16", "spconv_fwd_bf16", "affine_relu", "cast_pad", "bn_train_fwd", "bn_train_bwd", "col_sum", "dense", "dense_gather", "DenseFunction", "points_in_boxes_mask",
-    "points_in_any_box", "points_in_boxes_index", "boxes_bev", "nms", "box_trig_host", "box_trig4_host",
+    "points_in_any_box", "points_in_boxes_index", "boxes_bev", "nms", "centerhead_decode_nms", "box_trig_host", "box_trig4_host",
 ]
 
 
@@ -682,3 +682,33 @@ def nms(boxes, thresh, rotated=True, flavour="gpu", trig=None):
     check(lib.comb_nms(_p(boxes), _p(trig), n, float(thresh), int(bool(rotated)), 0 if flavour == "cpu" else 1,
                        _p(keep), _p(num), _p(ws), ws.numel(), _stream()), "comb_nms")
     return keep, num
+
+
+def centerhead_decode_nms(hm, center, center_z, dim, rot, K, feature_map_stride, voxel_size, point_cloud_range,
+                          post_center_limit_range, score_thresh, nms_thresh, nms_pre_max, nms_post_max, label_map=None):
+    """One separate head of CenterHead.generate_predicted_boxes on the device (comb_centerhead_decode_nms).
+    hm / dim are the RAW head outputs.  -> (boxes (B,K,7), scores (B,K), labels (B,K) int32 1-based, counts (B,) int32),
+    capacity-sized with the per-frame counts on the device."""
+    lib = _lib.load()
+    for n_, t_ in (("hm", hm), ("center", center), ("center_z", center_z), ("dim", dim), ("rot", rot)):
+        _need(t_, torch.float32, n_)
+    _need(label_map, torch.int32, "label_map")
+    B, C, H, W = [int(v) for v in hm.shape]
+    K = int(K)
+    dev = hm.device
+    boxes = torch.empty((B, K, 7), dtype=torch.float32, device=dev)
+    scores = torch.empty((B, K), dtype=torch.float32, device=dev)
+    labels = torch.empty((B, K), dtype=torch.int32, device=dev)
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    nbytes = lib.comb_centerhead_workspace_bytes(B, K)
+    if nbytes == 0:
+        raise RuntimeError("centerhead_decode_nms: K=%d outside [1,1024]" % K)
+    ws = _ws(nbytes, dev)
+    lim = (ctypes.c_float * 6)(*[float(v) for v in post_center_limit_range])
+    with _Scope("centerhead_decode_nms", B=B, C=C, H=H, W=W, K=K):
+        check(lib.comb_centerhead_decode_nms(
+            _p(hm), _p(center), _p(center_z), _p(dim), _p(rot), B, C, H, W, K, float(feature_map_stride),
+            float(voxel_size[0]), float(voxel_size[1]), float(point_cloud_range[0]), float(point_cloud_range[1]), lim,
+            float(score_thresh), _p(label_map), float(nms_thresh), int(nms_pre_max), int(nms_post_max), _p(boxes),
+            _p(scores), _p(labels), _p(counts), _p(ws), nbytes, _stream()), "comb_centerhead_decode_nms")
+    return boxes, scores, labels, counts

@@ -314,6 +314,30 @@ size_t comb_nms_workspace_bytes(int n);
 int comb_nms(const float* boxes, const float* trig, int n, float thresh, int rotated, int flavour,
              long long* keep, int* num_keep, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same with the number of boxes on the device: n_dev (may be NULL) holds the live count, n_max sizes the launch and
+ * the workspace — for callers whose box list is produced by a previous kernel (comb_centerhead_decode_nms). */
+int comb_nms_dev(const float* boxes, const float* trig, int n_max, const int* n_dev, float thresh, int rotated,
+                 int flavour, long long* keep, int* num_keep, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- f2: CenterHead post-processing ------------------------------------------------------------------------------
+ * Replaces CenterHead.generate_predicted_boxes (pcdet/models/dense_heads/center_head.py:266-317) =
+ * centernet_utils.decode_bbox_from_heatmap (pcdet/models/model_utils/centernet_utils.py:199-279: _topk, gathers,
+ * atan2 / exp / grid->metric decode, range + score mask) followed by model_nms_utils.class_agnostic_nms
+ * (model_nms_utils.py:6-25, NMS_TYPE nms_gpu) for one separate head, with no host round trip:
+ *   hm [B,C,H,W] RAW logits (sigmoid is applied here), center [B,2,H,W], center_z [B,1,H,W], dim [B,3,H,W] RAW (exp is
+ *   applied here), rot [B,2,H,W] = (cos, sin); all fp32 NCHW, contiguous.
+ *   K = MAX_OBJ_PER_SAMPLE (<= 1024); limit_range = POST_CENTER_LIMIT_RANGE (6 host floats); label_map (device, C
+ *   ints, may be NULL) = class_id_mapping_each_head of the head; labels come out 1-based like the reference's.
+ * Outputs are capacity-sized: out_boxes [B,K,7], out_scores [B,K], out_labels [B,K] int32, out_counts [B] int32 (the
+ * number of detections per frame, on the device).  workspace: comb_centerhead_workspace_bytes(B, K). */
+size_t comb_centerhead_workspace_bytes(int B, int K);
+int comb_centerhead_decode_nms(const float* hm, const float* center, const float* center_z, const float* dim,
+                               const float* rot, int B, int C, int H, int W, int K, float stride, float vx, float vy,
+                               float rx, float ry, const float* limit_range, float score_thresh, const int* label_map,
+                               float nms_thresh, int nms_pre_max, int nms_post_max, float* out_boxes,
+                               float* out_scores, int* out_labels, int* out_counts, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
