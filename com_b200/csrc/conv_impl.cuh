@@ -1,7 +1,8 @@
 // Internal interface between the C-ABI entry points of the bf16 sparse convolution (conv_tc.cu) and its
-// implementations.  COMB_CONV_NARROW=wm sends the narrow levels (Cin, Cout <= 32) to the experimental warp-level mma.sync
-// kernel of conv_wm.cu (measured slower, not the default); everything else runs one of the two tcgen05 kernels: "ts" (A operand gathered into tensor memory, conv_ts.cu — the default) and "ss"
-// (A operand gathered into shared memory, conv_tc.cu — kept for A/B measurements, COMB_CONV_IMPL=ss).
+// implementations, the two tcgen05 kernels: "ts" (A operand gathered into tensor memory, conv_ts.cu — the default) and
+// "ss" (A operand gathered into shared memory, conv_tc.cu — kept for A/B measurements, COMB_CONV_IMPL=ss).  (The r1
+// warp-level mma.sync experiment for the narrow levels, measured slower, lives in scripts/micro/conv_wm.cu and is no
+// longer part of the product library.)
 // The packed weight image differs between the two (the ts form permutes K inside a chunk), so the choice is
 // made once per process and used by both comb_spconv_pack_weight_bf16 and comb_spconv_fwd_bf16.
 #pragma once
@@ -27,15 +28,12 @@ struct ConvFwdArgs {
   int blocked = 0;  // conv_ts: contiguous super-tile range per CTA (1) or strided assignment (0, default)
   int ni = 4;       // conv_ts: index-tile ring depth (set by launch_ts)
   int nb = 0;       // conv_ts: streamed-weight stages (set by launch_ts)
+  int sc = 2;       // conv_ts: chunks of each row tile per A stage (set by launch_ts)
 };
 
 int ts_fwd_bf16(const ConvFwdArgs& p, int Cin_p, int Cout, cudaStream_t stream);
 int ts_pack_weight(const float* weight, int Cout, int K, int Cin, int Cin_p, int nchunks, void* wpacked,
                    cudaStream_t stream);
 
-// narrow levels (Cin, Cout in {16, 32}): warp-level gather + mma.sync (conv_wm.cu)
-bool wm_supported(int Cin_p, int Cout);
-int wm_fwd_bf16(const ConvFwdArgs& p, int Cin_p, int Cout, cudaStream_t stream);
-int wm_pack_weight(const float* weight, int Cout, int K, int Cin, int Cin_p, void* wpacked, cudaStream_t stream);
 
 }  // namespace comb

@@ -527,17 +527,6 @@ static bool use_ts() {
   return v == 1;
 }
 
-// COMB_CONV_NARROW=wm moves the 16/32-channel levels to the warp-level mma.sync kernel of conv_wm.cu (A/B
-// measurements; r1: 45 / 87 us per 16x16 / 32x32 level-1/2 layer against 33 / 58 us on tcgen05, so it is NOT the default).
-static bool use_wm(int Cin_p, int Cout) {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("COMB_CONV_NARROW");
-    v = (e && e[0] == 'w' && e[1] == 'm') ? 1 : 0;
-  }
-  return v == 1 && wm_supported(Cin_p, Cout);
-}
-
 }  // namespace
 }  // namespace comb
 
@@ -562,7 +551,6 @@ extern "C" int comb_spconv_pack_weight_bf16(const float* weight, int Cout, int K
   COMB_CHECK_ARG(Cin >= 1 && Cin <= Cin_p, "comb_spconv_pack_weight_bf16: Cin %d > padded %d", Cin, Cin_p);
   COMB_CHECK_ARG(Cout % 8 == 0 && Cout >= 8 && K >= 1, "comb_spconv_pack_weight_bf16: bad Cout/K");
   const int nchunks = chunks_for(Cin_p, K);
-  if (use_wm(Cin_p, Cout)) return wm_pack_weight(weight, Cout, K, Cin, Cin_p, wpacked, stream);
   if (use_ts()) return ts_pack_weight(weight, Cout, K, Cin, Cin_p, nchunks, wpacked, stream);
   const long long total = (long long)nchunks * Cout * kChunkK;
   const int grid = cdiv(total, 256);
@@ -591,7 +579,7 @@ extern "C" int comb_spconv_fwd_bf16(const void* in_feats, int Cin_p, const void*
   COMB_CHECK_ARG(out_dtype == COMB_DT_F32 || out_dtype == COMB_DT_BF16, "comb_spconv_fwd_bf16: bad out dtype");
   if (no_max == 0) return COMB_OK;
   COMB_CHECK_ARG(in_feats && wpacked && nbr && out, "comb_spconv_fwd_bf16: null pointer");
-  if (use_ts() || use_wm(Cin_p, Cout)) {
+  if (use_ts()) {
     ConvFwdArgs a;
     a.in = (const __nv_bfloat16*)in_feats;
     a.wpacked = (const uint8_t*)wpacked;
@@ -608,7 +596,6 @@ extern "C" int comb_spconv_fwd_bf16(const void* in_feats, int Cin_p, const void*
     a.out = out;
     a.out_f32 = out_dtype == COMB_DT_F32;
     a.dbg = g_conv_trace;
-    if (use_wm(Cin_p, Cout)) return wm_fwd_bf16(a, Cin_p, Cout, stream);
     return ts_fwd_bf16(a, Cin_p, Cout, stream);
   }
   TcParams p;

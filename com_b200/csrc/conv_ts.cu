@@ -68,7 +68,7 @@ struct TsCfg {
   static __host__ __device__ bool b_resident(int K) { return num_chunks(K) * kBBytes <= kBResidentMax; }
   static __host__ __device__ int tiles_per_pass(int) { return 2; }   // T: every pass walks two row tiles, one per MMA-issuing thread
   // TMEM: accumulator ring in [0, d_cols), A stages of 128 columns (4 chunks) behind it
-  static __host__ __device__ int d_cols(int) { return COUT >= 64 ? 256 : 128; }
+  static __host__ __device__ int d_cols(int) { return COUT >= 128 ? 256 : 128; }   // 2 x 128, 2 x 64, 4 x 32, 4 x 16
   static __host__ __device__ int n_acc(int K) {
     const int n = d_cols(K) / COUT;
     return n > 4 ? 4 : n;
@@ -125,6 +125,14 @@ __device__ __forceinline__ void dbg_cta_time(long long* dbg, int slot) {   // pe
   }
 }
 
+// wait of a warp that is not on the MMA issue path: PIPE = 2 (COMB_TS_PIPE=2) polls with plain try_wait (the
+// instruction suspends the warp in hardware for a bounded time), everything else backs off with nanosleep
+template <int PIPE>
+__device__ __forceinline__ void wait_bg(uint32_t bar, uint32_t parity) {
+  if (PIPE == 2) mbar_wait(bar, parity);
+  else mbar_wait_sleep(bar, parity);
+}
+
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
@@ -155,7 +163,14 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   const int lNI = NI == 8 ? 3 : 2;
   const int NB = p.nb;                               // streamed-weight stages, chosen on the host
   const int ND = Cfg::n_acc(K);                      // accumulator ring (power of two, >= T)
-  const int NS = Cfg::a_stages(K);                   // A stages of 4 chunks
+  // A stage = SC chunks of EACH of the two row tiles of the pass (2*SC chunk slots of 32 TMEM columns).  r2: with
+  // every neighbour ABSENT — no global load at all — the 16x16 layer still takes 27.9 us against 28.6 us on the real
+  // rulebook (scripts/conv_floor.py): the hand-shakes of the pipeline, not the gather loads, bound the kernel.  Larger
+  // stages (SC = 3: 6 slots, 2 stages) were measured and did not help; SC = 2 (4 slots, 3 stages at Cout <= 64) is the
+  // default.
+  const int SC = p.sc;
+  const uint32_t stage_cols = (uint32_t)(2 * SC * 32);
+  const int NS = (512 - Cfg::d_cols(K)) / (int)stage_cols;     // A stages
   const uint32_t colA = (uint32_t)Cfg::d_cols(K);
   // Passes.  A pass walks T row tiles; with T = 2 the last wave of passes is split into single-tile passes when
   // that shortens it (r <= grid/2 leftover super-tiles become 2r half passes on 2r CTAs: the absent second tile
@@ -201,14 +216,13 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   } else {
     my_super = nsuper > (int)blockIdx.x ? (nsuper - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   }
-  const int CT = nchunks << lT;                      // chunk slots per super-tile, order (c, t)
-  const int nst = (CT + 3) >> 2;                     // stages per super-tile (the last one may be partial)
+  const int nst = (nchunks + SC - 1) / SC;           // stages per super-tile (the last one may be partial)
 
   // shared memory map (1024-byte aligned): [barriers 1 KB] [weights: resident image | NB streamed 2-chunk stages]
   // [index tiles NI x kpad x 128]
   const uint32_t bars = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = bars + 1024u;
-  const uint32_t idx_base = w_base + (bres ? nchunks * Cfg::kBBytes : NB * 2 * Cfg::kBBytes);
+  const uint32_t idx_base = w_base + (bres ? nchunks * Cfg::kBBytes : NB * SC * Cfg::kBBytes);
   const uint32_t idx_buf_bytes = (uint32_t)kpad * kBM * 4;
 
   if (tid == 0) {
@@ -244,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bars + kTmemSlot) : "memory");
   if (TRACE && tid == 0) dbg_cta_time(p.dbg, 1);
 
-  if (PIPE) {
+  if (PIPE == 1) {
     // Register budget: the CTA owns 768 x 80 = 61440 registers for its whole life (setmaxnreg only moves registers
     // inside the CTA's pool: asking for more than the other warpgroups release never completes — r2 lesson, a 104-register
     // request deadlocked).  The gather warps (warpgroups 0-3) hold two batches of 32 registers of loads in flight; the
@@ -272,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
     const __nv_bfloat16* in = p.in + 4 * j;
     const int t = grp & (T - 1);
     const uint32_t row_off = (uint32_t)(q * 32 + r8) * 4;           // + (h*16 + rr*8)*4 per row of the thread
-    const uint32_t ta0 = tmem_base + ((uint32_t)(q * 32) << 16) + colA + (uint32_t)(grp * 32);
+    const uint32_t ta0 = tmem_base + ((uint32_t)(q * 32) << 16) + colA + (uint32_t)(grp * 32);   // SC == 2 in this variant
     const int total = my_super * nst;
 
     int lit = 0, lst = 0;
@@ -382,47 +396,55 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       const int buf = n & (NI - 1);
       const bool absent = t == 1 && absent_of(it);
       const uint32_t idx_tile = idx_base + (uint32_t)buf * idx_buf_bytes;
-      mbar_wait_sleep(bars + kBarIdx + 8 * buf, (uint32_t)(n >> lNI) & 1u);   // also for an absent tile: its fill must have landed before the buffer is handed back
+      wait_bg<PIPE>(bars + kBarIdx + 8 * buf, (uint32_t)(n >> lNI) & 1u);   // also for an absent tile: its fill must have landed before the buffer is handed back
       for (int st = 0; st < nst; ++st, ++gst) {
-        const int c = 2 * st + (grp >> 1);             // x >> 1
-        const bool have = c < nchunks && !absent;
-        uint4 v[2][2][2];     // [16-lane half][row, row+8][piece]
-        if (TRACE && tr) dbg_stamp(p.dbg, gst, 2);
-        if (have) {
-          if (TRACE && tr) dbg_stamp(p.dbg, gst, 7);
-          const uint32_t idx_c = idx_tile +
-                                 (uint32_t)(CIN <= 64 ? c * Cfg::kOffPerChunk : c / Cfg::kChunksPerOff) * kBM * 4;
-          const int ehalf = CIN > 64 ? (c % Cfg::kChunksPerOff) * 64 : 0;
+        // this group's chunks of the stage: offsets hc = grp>>1, grp>>1 + 2, ... < SC inside the stage (tile t = grp & 1)
+        bool waited = false;
+        for (int hc = grp >> 1; hc < SC; hc += 2) {
+          const int c = SC * st + hc;
+          const bool have = c < nchunks && !absent;
+          uint4 v[2][2][2];     // [16-lane half][row, row+8][piece]
+          if (TRACE && tr) dbg_stamp(p.dbg, gst, 2);
+          if (have) {
+            if (TRACE && tr) dbg_stamp(p.dbg, gst, 7);
+            const uint32_t idx_c = idx_tile +
+                                   (uint32_t)(CIN <= 64 ? c * Cfg::kOffPerChunk : c / Cfg::kChunksPerOff) * kBM * 4;
+            const int ehalf = CIN > 64 ? (c % Cfg::kChunksPerOff) * 64 : 0;
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-              const int row = q * 32 + h * 16 + rr * 8 + r8;
-              int rw0, rw1;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw0) : "r"(idx_c + (uint32_t)(slot0 * kBM + row) * 4) : "memory");
-              if (CIN <= 32) {
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw1) : "r"(idx_c + (uint32_t)(slot1 * kBM + row) * 4) : "memory");
-              } else {
-                rw1 = rw0;
+              for (int rr = 0; rr < 2; ++rr) {
+                const int row = q * 32 + h * 16 + rr * 8 + r8;
+                int rw0, rw1;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw0) : "r"(idx_c + (uint32_t)(slot0 * kBM + row) * 4) : "memory");
+                if (CIN <= 32) {
+                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw1) : "r"(idx_c + (uint32_t)(slot1 * kBM + row) * 4) : "memory");
+                } else {
+                  rw1 = rw0;
+                }
+                v[h][rr][0] = make_uint4(0u, 0u, 0u, 0u);
+                v[h][rr][1] = make_uint4(0u, 0u, 0u, 0u);
+                // (r1 A/B: 8-byte loads that land directly in the register pairs of the tcgen05.st fragment remove the 32
+                // register moves per chunk but double the load instructions: 5 % SLOWER, the LSU is the next limit)
+                if (rw0 >= 0) v[h][rr][0] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)(uint32_t)rw0 * CIN + ehalf + eo0));
+                if (rw1 >= 0) v[h][rr][1] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)(uint32_t)rw1 * CIN + ehalf + eo1));
               }
-              v[h][rr][0] = make_uint4(0u, 0u, 0u, 0u);
-              v[h][rr][1] = make_uint4(0u, 0u, 0u, 0u);
-              // (r1 A/B: 8-byte loads that land directly in the register pairs of the tcgen05.st fragment remove the 32
-              // register moves per chunk but double the load instructions: 5 % SLOWER, the LSU is the next limit)
-              if (rw0 >= 0) v[h][rr][0] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)(uint32_t)rw0 * CIN + ehalf + eo0));
-              if (rw1 >= 0) v[h][rr][1] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)(uint32_t)rw1 * CIN + ehalf + eo1));
-            }
+          }
+          if (!waited) {
+            wait_bg<PIPE>(bars + kBarEmpty + 8 * s, ph ^ 1u);
+            waited = true;
+          }
+          if (TRACE && tr) dbg_stamp(p.dbg, gst, 3);
+          if (have) {
+            tc_fence_after();
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + colA + (uint32_t)s * stage_cols + (uint32_t)((2 * hc + t) * 32);
+            tmem_st_16x256b_x4(ta, v[0][0][0], v[0][1][0], v[0][0][1], v[0][1][1]);
+            tmem_st_16x256b_x4(ta + (16u << 16), v[1][0][0], v[1][1][0], v[1][0][1], v[1][1][1]);
+          }
         }
-        mbar_wait_sleep(bars + kBarEmpty + 8 * s, ph ^ 1u);
-        if (TRACE && tr) dbg_stamp(p.dbg, gst, 3);
-        if (have) {
-          tc_fence_after();
-          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + colA + (uint32_t)((s * 4 + grp) * 32);
-          tmem_st_16x256b_x4(ta, v[0][0][0], v[0][1][0], v[0][0][1], v[0][1][1]);
-          tmem_st_16x256b_x4(ta + (16u << 16), v[1][0][0], v[1][1][0], v[1][0][1], v[1][1][1]);
-          tmem_st_wait();
-          tc_fence_before();
-        }
+        if (!waited) wait_bg<PIPE>(bars + kBarEmpty + 8 * s, ph ^ 1u);     // a group without a chunk in this stage (SC = 1)
+        tmem_st_wait();
+        tc_fence_before();
         if (lane == 0) mbar_arrive(bars + kBarFull + 8 * s);
         if (TRACE && tr) dbg_stamp(p.dbg, gst, 4);
         if (++s == NS) { s = 0; ph ^= 1u; }
@@ -447,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
         rv[0] = __ldg(rp);
         rv[1] = __ldg(rp + 1);
       }
-      mbar_wait_sleep(bars + kBarTFull + 8 * a, (uint32_t)(n / ND) & 1u);
+      wait_bg<PIPE>(bars + kBarTFull + 8 * a, (uint32_t)(n / ND) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * COUT;
 #pragma unroll
@@ -525,56 +547,61 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
     const int my_t = warp == kMmaWarp ? 0 : 1;
     if (elect_one_sync()) {
-      int s = 0, bs = 0, it = 0, st = 0;
+      int s = 0, bs = 0, gst = 0;
       uint32_t ph = 0, bph = 0;
       bool ready = false;
       if (bres) mbar_wait(bars + kBarB, 0);
-      const int total = my_super * nst;
-      for (int gst = 0; gst < total; ++gst) {
+      // per pass: my tile's accumulator and whether the tile exists; per stage only ring arithmetic (the loop nest keeps
+      // the live state of this thread small: its issue loop is the critical path of the kernel)
+      for (int it = 0; it < my_super; ++it) {
         const int n = (it << lT) + my_t;              // tile sequence number of my tile in this pass
-        if (TRACE && my_t == 0) dbg_stamp(p.dbg, gst, 6);
-        if (!ready) {
-          if (st == 0) mbar_wait(bars + kBarTEmpty + 8 * (n & (ND - 1)), ((uint32_t)(n / ND) & 1u) ^ 1u);
-          if (!bres) mbar_wait(bars + kBarBFull + 8 * bs, bph);
-          mbar_wait(bars + kBarFull + 8 * s, ph);
-        }
-        if (TRACE && my_t == 0) dbg_stamp(p.dbg, gst, 0);
-        tc_fence_after();
-        // ring positions of the next stage
-        const int s2 = s + 1 == NS ? 0 : s + 1;
-        const uint32_t ph2 = s + 1 == NS ? ph ^ 1u : ph;
-        const int bs2 = bs + 1 == NB ? 0 : bs + 1;
-        const uint32_t bph2 = bs + 1 == NB ? bph ^ 1u : bph;
-        const bool last_st = st == nst - 1;
         const bool absent = my_t == 1 && absent_of(it);   // single-tile pass
-        const uint32_t tmem_d = tmem_base + (uint32_t)((n & (ND - 1)) * COUT);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = 2 * st + h;                   // my chunk slot of the stage: sub = 2*h + my_t
-          if (c < nchunks && !absent) {
-            const uint32_t tmem_a = tmem_base + colA + (uint32_t)((s * 4 + 2 * h + my_t) * 32);
-            const uint64_t bdesc = make_desc_sw128(w_base + (uint32_t)(bres ? c : bs * 2 + h) * Cfg::kBBytes);
-#pragma unroll
-            for (int kk = 0; kk < kChunkK / 16; ++kk)
-              umma_bf16_ts(tmem_d, tmem_a + 8 * kk, bdesc + 2 * kk, idesc, (c | kk) != 0 ? 1u : 0u);
+        const uint32_t acc = (uint32_t)(n & (ND - 1));
+        const uint32_t tmem_d = tmem_base + acc * COUT;
+        const uint32_t acc_ph = (uint32_t)(n / ND) & 1u;
+        const bool last_pass = it == my_super - 1;
+        for (int st = 0; st < nst; ++st, ++gst) {
+          if (TRACE && my_t == 0) dbg_stamp(p.dbg, gst, 6);
+          if (!ready) {
+            if (st == 0) mbar_wait(bars + kBarTEmpty + 8 * acc, acc_ph ^ 1u);
+            if (!bres) mbar_wait(bars + kBarBFull + 8 * bs, bph);
+            mbar_wait(bars + kBarFull + 8 * s, ph);
           }
-          if (h == 0) {   // probe the next stage while the second chunk of this one is still to be issued
-            ready = gst + 1 < total && mbar_test(bars + kBarFull + 8 * s2, ph2);
-            if (!bres) ready = ready && mbar_test(bars + kBarBFull + 8 * bs2, bph2);
-            if (last_st) {
-              const int n2 = n + T;
-              ready = ready && mbar_test(bars + kBarTEmpty + 8 * (n2 & (ND - 1)), ((uint32_t)(n2 / ND) & 1u) ^ 1u);
+          if (TRACE && my_t == 0) dbg_stamp(p.dbg, gst, 0);
+          tc_fence_after();
+          // ring positions of the next stage
+          const int s2 = s + 1 == NS ? 0 : s + 1;
+          const uint32_t ph2 = s + 1 == NS ? ph ^ 1u : ph;
+          const int bs2 = bs + 1 == NB ? 0 : bs + 1;
+          const uint32_t bph2 = bs + 1 == NB ? bph ^ 1u : bph;
+          const bool last_st = st == nst - 1;
+          const uint32_t a_stage = tmem_base + colA + (uint32_t)s * stage_cols + (uint32_t)(my_t * 32);
+          for (int h = 0; h < SC; ++h) {
+            const int c = SC * st + h;                  // my chunk of the stage: slot 2*h + my_t
+            if (c < nchunks && !absent) {
+              const uint32_t tmem_a = a_stage + (uint32_t)(h * 64);
+              const uint64_t bdesc = make_desc_sw128(w_base + (uint32_t)(bres ? c : bs * SC + h) * Cfg::kBBytes);
+#pragma unroll
+              for (int kk = 0; kk < kChunkK / 16; ++kk)
+                umma_bf16_ts(tmem_d, tmem_a + 8 * kk, bdesc + 2 * kk, idesc, (c | kk) != 0 ? 1u : 0u);
+            }
+            if (h == 0) {   // probe the next stage while the other chunks of this one are still to be issued
+              ready = !(last_pass && last_st) && mbar_test(bars + kBarFull + 8 * s2, ph2);
+              if (!bres) ready = ready && mbar_test(bars + kBarBFull + 8 * bs2, bph2);
+              if (last_st) {
+                const int n2 = n + T;
+                ready = ready && mbar_test(bars + kBarTEmpty + 8 * (n2 & (ND - 1)), ((uint32_t)(n2 / ND) & 1u) ^ 1u);
+              }
             }
           }
+          umma_commit(bars + kBarEmpty + 8 * s);
+          if (!bres) umma_commit(bars + kBarBEmpty + 8 * bs);
+          if (last_st) umma_commit(bars + kBarTFull + 8 * acc);
+          if (TRACE && my_t == 0) dbg_stamp(p.dbg, gst, 1);
+          s = s2;
+          ph = ph2;
+          if (!bres) { bs = bs2; bph = bph2; }
         }
-        umma_commit(bars + kBarEmpty + 8 * s);
-        if (!bres) umma_commit(bars + kBarBEmpty + 8 * bs);
-        if (last_st) umma_commit(bars + kBarTFull + 8 * (n & (ND - 1)));
-        if (TRACE && my_t == 0) dbg_stamp(p.dbg, gst, 1);
-        s = s2;
-        ph = ph2;
-        if (!bres) { bs = bs2; bph = bph2; }
-        if (last_st) { st = 0; ++it; } else { ++st; }
       }
     }
     __syncwarp();
@@ -586,7 +613,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
     for (int n = 0; n < ntile_seq; ++n) {
       const int buf = n & (NI - 1);
       const int use = n >> lNI;            // how many times this buffer has been filled before
-      if (use > 0) mbar_wait_sleep(bars + kBarIdxFree + 8 * buf, (uint32_t)(use - 1) & 1u);
+      if (use > 0) wait_bg<PIPE>(bars + kBarIdxFree + 8 * buf, (uint32_t)(use - 1) & 1u);
       const int tile = tile_of(n);
       const int row0 = tile * kBM + lane * 4;   // this lane: 4 consecutive rows
       const uint32_t dst = idx_base + (uint32_t)buf * idx_buf_bytes + lane * 16;
@@ -614,16 +641,16 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       mbar_arrive_expect_tx(bars + kBarB, bytes);
       bulk_copy_g2s(w_base, p.wpacked, bytes, bars + kBarB);
     } else {
-      // one 2-chunk weight stage per A stage (T = 2: a stage is chunks 2*st, 2*st+1 for both row tiles)
+      // one SC-chunk weight stage per A stage (a stage is chunks SC*st .. SC*st+SC-1 for both row tiles)
       int bs = 0;
       uint32_t bph = 0;
       for (int it = 0; it < my_super; ++it)
         for (int st = 0; st < nst; ++st) {
-          const int c0 = 2 * st;
-          const uint32_t bytes = (uint32_t)(nchunks - c0 < 2 ? nchunks - c0 : 2) * Cfg::kBBytes;
+          const int c0 = SC * st;
+          const uint32_t bytes = (uint32_t)(nchunks - c0 < SC ? nchunks - c0 : SC) * Cfg::kBBytes;
           mbar_wait(bars + kBarBEmpty + 8 * bs, bph ^ 1u);
           mbar_arrive_expect_tx(bars + kBarBFull + 8 * bs, bytes);
-          bulk_copy_g2s(w_base + bs * 2 * Cfg::kBBytes, p.wpacked + (size_t)c0 * Cfg::kBBytes, bytes, bars + kBarBFull + 8 * bs);
+          bulk_copy_g2s(w_base + bs * SC * Cfg::kBBytes, p.wpacked + (size_t)c0 * Cfg::kBBytes, bytes, bars + kBarBFull + 8 * bs);
           if (++bs == NB) { bs = 0; bph ^= 1u; }
         }
     }
@@ -691,17 +718,27 @@ int launch_ts(const ConvFwdArgs& p_in, cudaStream_t stream) {
   static const int ni_env = env_int("COMB_TS_NI", 4), nb_env = env_int("COMB_TS_NB", 4), blocked_env = env_int("COMB_TS_BLOCKED", 0);
   p.blocked = blocked_env;
   p.ni = (ni_env == 8 && Cfg::n_idx(p.K) == 8) ? 8 : 4;
+  // chunks of each row tile per A stage.  r2 A/B (gpu_r2_m): SC = 3 where tensor memory allows (6 slots, 2 stages)
+  // against SC = 2 (4 slots, 3 stages): 1.018 vs 0.997 ms of conv per step — the larger stage does not pay, the default
+  // stays 2 (COMB_TS_SC=1..3 to override; the pipelined-gather variant is written for SC = 2)
+  static const int sc_env = env_int("COMB_TS_SC", 2);
+  int sc_max = (512 - Cfg::d_cols(p.K)) / (2 * 2 * 32);      // 2 stages x 2 tiles x 32 columns per chunk slot
+  if (sc_max > 3) sc_max = 3;
+  int sc = sc_env >= 1 && sc_env <= sc_max ? sc_env : 2;
+  if (ts_pipe() == 1) sc = 2;
+  p.sc = sc;
   const int idx_bytes = p.ni * Cfg::k_pad(p.K) * kBM * 4;
   const bool bres = Cfg::b_resident(p.K);
-  int nb = bres ? 0 : (kSmemBudget - 2048 - idx_bytes) / (2 * Cfg::kBBytes);
+  int nb = bres ? 0 : (kSmemBudget - 2048 - idx_bytes) / (sc * Cfg::kBBytes);
   if (nb > kMaxBStages) nb = kMaxBStages;
   if (!bres && nb > nb_env && nb_env >= 2) nb = nb_env;
   p.nb = nb;
-  const size_t smem = 2048 + (size_t)idx_bytes + (bres ? (size_t)Cfg::num_chunks(p.K) * Cfg::kBBytes : (size_t)nb * 2 * Cfg::kBBytes);
+  const size_t smem = 2048 + (size_t)idx_bytes + (bres ? (size_t)Cfg::num_chunks(p.K) * Cfg::kBBytes : (size_t)nb * sc * Cfg::kBBytes);
   static thread_local DevOnce configured;   // per device: the attribute is a per-device property
   if (configured.first()) {
     COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
     COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
     COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
   }
   if (smem > 227 * 1024 - 1024 || (!bres && nb < 2)) {
@@ -712,6 +749,7 @@ int launch_ts(const ConvFwdArgs& p_in, cudaStream_t stream) {
   const int grid = nsuper < sm_count() ? nsuper : sm_count();
   if (p.dbg != nullptr) spconv_ts_kernel<CIN, COUT, true, 0><<<grid, kThreads, smem, stream>>>(p);   // pipeline trace build
   else if (ts_pipe() == 1) spconv_ts_kernel<CIN, COUT, false, 1><<<grid, kThreads, smem, stream>>>(p);
+  else if (ts_pipe() == 2) spconv_ts_kernel<CIN, COUT, false, 2><<<grid, kThreads, smem, stream>>>(p);
   else spconv_ts_kernel<CIN, COUT, false, 0><<<grid, kThreads, smem, stream>>>(p);
   COMB_LAUNCH_CHECK();
   return COMB_OK;
