@@ -29,11 +29,16 @@ struct ConvFwdArgs {
   int ni = 4;       // conv_ts: index-tile ring depth (set by launch_ts)
   int nb = 0;       // conv_ts: streamed-weight stages (set by launch_ts)
   int sc = 2;       // conv_ts: chunks of each row tile per A stage (set by launch_ts)
+  int ablate = 0;   // conv_ts: COMB_TS_ABLATE bit mask — pipeline pieces switched off for timing experiments (results are garbage)
 };
 
 int ts_fwd_bf16(const ConvFwdArgs& p, int Cin_p, int Cout, cudaStream_t stream);
-int ts_pack_weight(const float* weight, int Cout, int K, int Cin, int Cin_p, int nchunks, void* wpacked,
+// natural: K in tap-major / channel-minor order (conv_tr.cu and the pipelined conv_ts variant); otherwise the permuted
+// order of the tcgen05.st.16x256b fragment (conv_ts.cu)
+int ts_pack_weight(const float* weight, int Cout, int K, int Cin, int Cin_p, int nchunks, int natural, void* wpacked,
                    cudaStream_t stream);
+// row-per-thread form (conv_tr.cu)
+int tr_fwd_bf16(const ConvFwdArgs& p, int Cin_p, int Cout, cudaStream_t stream);
 
 
 }  // namespace comb

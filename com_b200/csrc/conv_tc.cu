@@ -517,14 +517,28 @@ static int chunks_for(int Cin_p, int K) {
   return Cin_p <= 64 ? (K + 64 / Cin_p - 1) / (64 / Cin_p) : K * (Cin_p / 64);
 }
 
-// COMB_CONV_IMPL=ss selects the shared-memory-A kernel of this file; the default is the tensor-memory-A kernel.
-static bool use_ts() {
+// COMB_CONV_IMPL: "ss" = the shared-memory-A kernel of this file, "ts" = tensor-memory A gathered in 16x256b fragments
+// (conv_ts.cu) for every layer, "tr" = the row-per-thread kernel (conv_tr.cu) for every layer; unset = per layer, see
+// use_tr().  Read once per process: the packed weight image depends on it.
+static int conv_impl() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("COMB_CONV_IMPL");
-    v = (e && e[0] == 's' && e[1] == 's') ? 0 : 1;
+    v = 0;                                              // auto
+    if (e && e[0] == 's' && e[1] == 's') v = 1;
+    else if (e && e[0] == 't' && e[1] == 's') v = 2;
+    else if (e && e[0] == 't' && e[1] == 'r') v = 3;
   }
-  return v == 1;
+  return v;
+}
+static bool use_ts() { return conv_impl() != 1; }       // "one of the tensor-memory kernels"
+// which tensor-memory kernel runs a layer; the same predicate decides the layout of its packed weights
+static bool use_tr(int Cin_p, int Cout, int K) {
+  (void)Cout;
+  (void)K;
+  if (conv_impl() == 3) return true;
+  if (conv_impl() == 2) return false;
+  return false;
 }
 
 }  // namespace
@@ -551,7 +565,7 @@ extern "C" int comb_spconv_pack_weight_bf16(const float* weight, int Cout, int K
   COMB_CHECK_ARG(Cin >= 1 && Cin <= Cin_p, "comb_spconv_pack_weight_bf16: Cin %d > padded %d", Cin, Cin_p);
   COMB_CHECK_ARG(Cout % 8 == 0 && Cout >= 8 && K >= 1, "comb_spconv_pack_weight_bf16: bad Cout/K");
   const int nchunks = chunks_for(Cin_p, K);
-  if (use_ts()) return ts_pack_weight(weight, Cout, K, Cin, Cin_p, nchunks, wpacked, stream);
+  if (use_ts()) return ts_pack_weight(weight, Cout, K, Cin, Cin_p, nchunks, use_tr(Cin_p, Cout, K) ? 1 : 0, wpacked, stream);
   const long long total = (long long)nchunks * Cout * kChunkK;
   const int grid = cdiv(total, 256);
   __nv_bfloat16* out = (__nv_bfloat16*)wpacked;
@@ -596,6 +610,7 @@ extern "C" int comb_spconv_fwd_bf16(const void* in_feats, int Cin_p, const void*
     a.out = out;
     a.out_f32 = out_dtype == COMB_DT_F32;
     a.dbg = g_conv_trace;
+    if (use_tr(Cin_p, Cout, K)) return tr_fwd_bf16(a, Cin_p, Cout, stream);
     return ts_fwd_bf16(a, Cin_p, Cout, stream);
   }
   TcParams p;

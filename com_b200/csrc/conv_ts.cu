@@ -390,6 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
     int s = 0, gst = 0;
     uint32_t ph = 0;
     const int t = grp & (T - 1);          // chunk slot x = 4*st + grp of a stage belongs to row tile x & 1 = grp & 1
+    const int AB = p.ablate;
     for (int it = 0; it < my_super; ++it) {
       // per pass: this warp's tile, its index buffer (waited for once), whether the tile exists
       const int n = (it << lT) + t;                    // tile sequence number of this CTA
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
           const bool have = c < nchunks && !absent;
           uint4 v[2][2][2];     // [16-lane half][row, row+8][piece]
           if (TRACE && tr) dbg_stamp(p.dbg, gst, 2);
-          if (have) {
+          if (have && !(AB & 4)) {
             if (TRACE && tr) dbg_stamp(p.dbg, gst, 7);
             const uint32_t idx_c = idx_tile +
                                    (uint32_t)(CIN <= 64 ? c * Cfg::kOffPerChunk : c / Cfg::kChunksPerOff) * kBM * 4;
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
             waited = true;
           }
           if (TRACE && tr) dbg_stamp(p.dbg, gst, 3);
-          if (have) {
+          if (have && !(AB & 6)) {
             tc_fence_after();
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + colA + (uint32_t)s * stage_cols + (uint32_t)((2 * hc + t) * 32);
             tmem_st_16x256b_x4(ta, v[0][0][0], v[0][1][0], v[0][0][1], v[0][1][1]);
@@ -472,6 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       wait_bg<PIPE>(bars + kBarTFull + 8 * a, (uint32_t)(n / ND) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * COUT;
+      if (!(p.ablate & 8))
 #pragma unroll
       for (int c0 = 0; c0 < COUT; c0 += 16) {
         uint32_t v[16];
@@ -546,6 +548,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
     // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B, N>>3 [17,23), M>>4 [24,29)
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
     const int my_t = warp == kMmaWarp ? 0 : 1;
+    const int AB = p.ablate;
     if (elect_one_sync()) {
       int s = 0, bs = 0, gst = 0;
       uint32_t ph = 0, bph = 0;
@@ -578,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
           const uint32_t a_stage = tmem_base + colA + (uint32_t)s * stage_cols + (uint32_t)(my_t * 32);
           for (int h = 0; h < SC; ++h) {
             const int c = SC * st + h;                  // my chunk of the stage: slot 2*h + my_t
-            if (c < nchunks && !absent) {
+            if (c < nchunks && !absent && !(AB & 1)) {
               const uint32_t tmem_a = a_stage + (uint32_t)(h * 64);
               const uint64_t bdesc = make_desc_sw128(w_base + (uint32_t)(bres ? c : bs * SC + h) * Cfg::kBBytes);
 #pragma unroll
@@ -586,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
                 umma_bf16_ts(tmem_d, tmem_a + 8 * kk, bdesc + 2 * kk, idesc, (c | kk) != 0 ? 1u : 0u);
             }
             if (h == 0) {   // probe the next stage while the other chunks of this one are still to be issued
-              ready = !(last_pass && last_st) && mbar_test(bars + kBarFull + 8 * s2, ph2);
+              ready = !(last_pass && last_st) && !(AB & 32) && mbar_test(bars + kBarFull + 8 * s2, ph2);
               if (!bres) ready = ready && mbar_test(bars + kBarBFull + 8 * bs2, bph2);
               if (last_st) {
                 const int n2 = n + T;
@@ -617,7 +620,8 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       const int tile = tile_of(n);
       const int row0 = tile * kBM + lane * 4;   // this lane: 4 consecutive rows
       const uint32_t dst = idx_base + (uint32_t)buf * idx_buf_bytes + lane * 16;
-      if (vec_ok && row0 + 3 < no) {
+      if (p.ablate & 16) {
+      } else if (vec_ok && row0 + 3 < no) {
         for (int k = 0; k < K; ++k)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + k * kBM * 4),
                        "l"(p.nbr + (size_t)k * p.ld + row0)
@@ -727,6 +731,10 @@ int launch_ts(const ConvFwdArgs& p_in, cudaStream_t stream) {
   int sc = sc_env >= 1 && sc_env <= sc_max ? sc_env : 2;
   if (ts_pipe() == 1) sc = 2;
   p.sc = sc;
+  {
+    const char* ab = getenv("COMB_TS_ABLATE");     // read per launch: timing experiments flip it inside one process
+    p.ablate = ab ? atoi(ab) : 0;
+  }
   const int idx_bytes = p.ni * Cfg::k_pad(p.K) * kBM * 4;
   const bool bres = Cfg::b_resident(p.K);
   int nb = bres ? 0 : (kSmemBudget - 2048 - idx_bytes) / (sc * Cfg::kBBytes);
@@ -781,12 +789,12 @@ int ts_fwd_bf16(const ConvFwdArgs& p, int Cin_p, int Cout, cudaStream_t stream) 
   return COMB_EINVAL;
 }
 
-int ts_pack_weight(const float* weight, int Cout, int K, int Cin, int Cin_p, int nchunks, void* wpacked,
+int ts_pack_weight(const float* weight, int Cout, int K, int Cin, int Cin_p, int nchunks, int natural_in, void* wpacked,
                    cudaStream_t stream) {
   const long long total = (long long)nchunks * Cout * kChunkK;
   const int grid = cdiv(total, 256);
   __nv_bfloat16* out = (__nv_bfloat16*)wpacked;
-  const int natural = ts_pipe() == 1 ? 1 : 0;   // the pipelined gather keeps K in its natural order
+  const int natural = (natural_in || ts_pipe() == 1) ? 1 : 0;   // the pipelined gather keeps K in its natural order
   switch (Cin_p) {
     case 16: ts_pack_kernel<16><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, natural, out); break;
     case 32: ts_pack_kernel<32><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, natural, out); break;
