@@ -39,6 +39,7 @@ int ts_pack_weight(const float* weight, int Cout, int K, int Cin, int Cin_p, int
                    cudaStream_t stream);
 // row-per-thread form (conv_tr.cu)
 int tr_fwd_bf16(const ConvFwdArgs& p, int Cin_p, int Cout, cudaStream_t stream);
+bool tr_supported(int Cin_p, int Cout, int K);     // weight image fits in shared memory
 
 
 }  // namespace comb

@@ -534,11 +534,11 @@ static int conv_impl() {
 static bool use_ts() { return conv_impl() != 1; }       // "one of the tensor-memory kernels"
 // which tensor-memory kernel runs a layer; the same predicate decides the layout of its packed weights
 static bool use_tr(int Cin_p, int Cout, int K) {
-  (void)Cout;
-  (void)K;
-  if (conv_impl() == 3) return true;
+  if (conv_impl() == 3) return tr_supported(Cin_p, Cout, K);
   if (conv_impl() == 2) return false;
-  return false;
+  // auto: the row-per-thread kernel for the narrow inputs (r2, bench frames: 22.5 vs 29.4 us at 16x16, 45.6 vs 49.6 at
+  // 32x32; at Cin = 64 the 16x256b gather of conv_ts is faster, 48 vs 67 us)
+  return Cin_p <= 32 && tr_supported(Cin_p, Cout, K);
 }
 
 }  // namespace

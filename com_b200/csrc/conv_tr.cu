@@ -3,31 +3,32 @@
 // Replaces the gather-GEMM-scatter of spconv's SubMConv3d / SparseConv3d forward
 // (pcdet/models/backbones_3d/spconv_backbone.py:191-232), same output-stationary implicit GEMM as conv_ts.cu
 //
-//   D[128 rows, Cout] (TMEM, fp32)  +=  A_slab[128, taps x Cin] (TMEM, bf16)  x  B[Cout, taps x Cin]^T (smem, bf16)
+//   D[128 rows, Cout] (TMEM, fp32)  +=  A_slab[128, up to 448] (TMEM, bf16)  x  B[Cout, up to 448]^T (smem, bf16)
 //
-// but built around what the r2 micro-benchmarks measured (scripts/micro/commit_bench.cu, profiles/r2_commit_bench.txt):
+// but built around what the r2 micro-benchmarks measured (scripts/micro/*.cu, profiles/r2_micro_*.txt):
 //  * the tensor pipe retires an M=128, K=16 MMA in 128*N/256 cycles (9 at N=16, 16 at N=32, 32 at N=64, 64 at N=128)
-//    when the issuing thread feeds it from uniform registers; tcgen05.commit costs nothing on top;
-//  * ONE producer/consumer barrier round costs the issuing thread ~300 cycles whatever the ring depth.  conv_ts.cu pays
-//    a round per 4 chunk slots with 16 gather warps arriving on every one of them: with everything but the hand-shakes
-//    switched off (COMB_TS_ABLATE=29) its 16x16 layer still takes 22 of its 32 us.
-// So here the unit of hand-shake is a SLAB: a run of whole kernel taps of one 128-row tile (14 taps at Cin = 16, 7 at
-// Cin = 32, 3 at Cin = 64, 1 at Cin = 128) that one group of four gather warps fills on its own:
-//  * thread t of gather warp w owns output row 32*(w%4) + t of the tile (= TMEM lane): it reads its neighbour indices
-//    straight from the rulebook (coalesced: 32 consecutive rows of one tap are 128 contiguous bytes; no index tile in
-//    shared memory, no index warp), loads each present neighbour's feature row with 32-byte loads (LDG.256; an absent
-//    neighbour reads a shared zero row instead of predicating and zero-filling registers) and writes it to its lane
-//    with tcgen05.st.32x32b — K stays in its natural order (tap-major, channel-minor), the weight image is the plain
-//    K-major SWIZZLE_128B image;
-//  * gather group g (warps 4g..4g+3) fills slot g of a ring of 4 slabs; the next slab's indices are fetched while the
-//    current slab's rows are in flight;
-//  * one elected thread issues the slab's MMAs back to back and commits once per slab (to the slot's empty barrier;
-//    after the last slab of a tile also to the accumulator's full barrier); accumulators are double buffered so the
+//    when the issuing thread feeds it from uniform registers, and tcgen05.commit costs nothing on top;
+//  * a barrier round costs the issuing thread 180-240 cycles of try_wait latency however deep the ring is, so the
+//    thread that issues the MMAs — not the tensor pipe, not the gather — bounds a kernel that hand-shakes often:
+//    conv_ts.cu pays a round per 4 chunk slots; with everything but its hand-shakes switched off (COMB_TS_ABLATE=29)
+//    its 16x16 layer still takes 17 of its 29 us;
+//  * what bounds the gather is bytes in flight (registers), not instructions.
+// So the unit of hand-shake here is a SLAB of up to 7 K-chunks (448 K positions: a whole 128-row tile at Cin = 16,
+// half a tile at Cin = 32), filled by ALL 16 gather warps at once, each with ONE batch of loads:
+//  * thread t of gather warp w owns output row 32*(w%4) + t of the tile (= TMEM lane) and quarter w/4 of the slab's
+//    K range: up to 7 pieces of 32 bytes (16 channels of one kernel tap).  It reads the neighbour index of each
+//    piece's tap straight from the rulebook (coalesced: 32 consecutive rows of a tap are 128 contiguous bytes; no
+//    index tile in shared memory, no index warp; the next slab's indices are fetched behind this slab's loads),
+//    loads the pieces with LDG.256 (an absent neighbour reads a shared zero row instead of predicating and
+//    zero-filling registers) and writes them to its lane with tcgen05.st.32x32b — K stays in its natural order
+//    (tap-major, channel-minor), the weight image is the plain K-major SWIZZLE_128B image;
+//  * one elected thread issues the slab's MMAs back to back (4 per chunk at constant descriptor offsets), commits the
+//    slot once per slab and probes the next slab's barrier while it issues; accumulators are double buffered so the
 //    epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// TMEM map (512 columns): [0, 2*Cout) two accumulators, then 4 slots of taps_per_slab * Cin/2 columns.
-// Weights: resident in shared memory when the image fits (<= 216 KB: everything up to 64x64), else streamed per slab
-// through a ring of cp.async.bulk stages.
+// TMEM map (512 columns): [0, 2*Cout) two accumulators, then 2 slots of 32 columns per chunk.
+// Weights: the whole image is resident in shared memory (one bulk copy per CTA): everything up to 64x64x27 fits in
+// 227 KB; the three wider shapes (64x128, 128x64, 128x128) stay on conv_ts.cu, which streams them (tr_supported()).
 #include <stdlib.h>
 #include "common.cuh"
 #include "conv_impl.cuh"
@@ -42,39 +43,24 @@ constexpr int kBM = 128;
 constexpr int kGatherWarps = 16;
 constexpr int kEpiWarp0 = 16;
 constexpr int kMmaWarp = 20;
-constexpr int kBWarp = 21;
-constexpr int kThreads = 22 * 32;      // 704 threads: 88 registers each
-constexpr int kSlots = 4;
+constexpr int kThreads = 21 * 32;      // registers are handed out per 4 warps: 21 warps cost as much as 24, 80 registers each
+constexpr int kSlots = 2;
 constexpr int kSmemMax = 227 * 1024;
-constexpr int kMaxBStages = 6;
+constexpr int kMaxPieces = 7;          // pieces (8 registers each) one gather thread holds in flight
 
 // 256 zero bytes: the "feature row" of an absent neighbour
 __device__ __align__(256) uint4 g_zero_row[16];
 
 template <int CIN, int COUT>
 struct TrCfg {
-  static constexpr int kTapCols = CIN / 2;                     // TMEM columns of one tap of one row
+  static constexpr int kPPT = CIN / 16;                        // 32-byte pieces per tap
+  static constexpr int kLogPPT = CIN == 16 ? 0 : CIN == 32 ? 1 : CIN == 64 ? 2 : 3;
   static constexpr int kAccCols = 2 * COUT;                    // two accumulators
-  static constexpr int kTpsMax = (512 - kAccCols) / kSlots / kTapCols;   // taps of a slab that fit in a slot
-  static constexpr int kSlotCols = kTpsMax * kTapCols;
+  static constexpr int kSlabChunksMax = (512 - kAccCols) / kSlots / 32 > kMaxPieces ? kMaxPieces : (512 - kAccCols) / kSlots / 32;
+  static constexpr int kSlotCols = kSlabChunksMax * 32;
   static constexpr int kBBytes = COUT * 128;                   // one 64-wide K chunk of the weight image
-  static constexpr int kTapRegs = CIN / 2;                     // registers of one tap of one row
-  static constexpr int kBatchRegs = CIN == 16 ? 40 : CIN == 32 ? 48 : 64;      // data registers of one batch of loads
-  static constexpr int kBatch = kTapRegs >= 64 ? 1 : kBatchRegs / kTapRegs > kTpsMax ? kTpsMax : kBatchRegs / kTapRegs;   // taps loaded together
-  static_assert(kTpsMax >= 1, "slab does not fit");
   static __host__ __device__ int num_chunks(int K) { return CIN <= 64 ? (K * CIN + 63) / 64 : K * (CIN / 64); }
-  static __host__ __device__ int slabs(int K) { return (K + kTpsMax - 1) / kTpsMax; }
-  // taps per slab, balanced over the slabs of a tile; with streamed weights a slab must cover whole 64-wide K chunks
-  static __host__ __device__ int tps(int K, bool resident) {
-    const int s = slabs(K);
-    int t = (K + s - 1) / s;
-    if (!resident) {
-      const int gran = CIN >= 64 ? 1 : 64 / CIN;
-      t = (t + gran - 1) / gran * gran;
-      if (t > kTpsMax) t = kTpsMax / gran * gran;
-    }
-    return t;
-  }
+  static __host__ __device__ int slabs(int K) { return (num_chunks(K) + kSlabChunksMax - 1) / kSlabChunksMax; }
   static __host__ __device__ bool resident(int K) { return (size_t)num_chunks(K) * kBBytes + 2048 <= (size_t)kSmemMax; }
 };
 
@@ -87,28 +73,11 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "l"(p));
 }
-
-// tcgen05.st.32x32b.xN: thread t writes N consecutive 32-bit columns of lane (32*(warp%4) + t)
-__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* v) {
+// tcgen05.st.32x32b.x8: thread t writes 8 consecutive 32-bit columns of lane (32*(warp%4) + t)
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
                "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
-}
-__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
-      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-template <int N>
-__device__ __forceinline__ void tmem_st_row(uint32_t taddr, const uint32_t* v) {
-  if constexpr (N == 8) {
-    tmem_st_x8(taddr, v);
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; i += 16) tmem_st_x16(taddr + i, v + i);
-  }
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -126,23 +95,20 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tr_kernel(ConvFwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int no = eff_n(p.no_max, p.no_dev);             // real row count: only the gather and the epilogue look at it
-  const int ntiles = (p.no_max + kBM - 1) / kBM;        // loop structure of every role: the launch bound (uniform)
+  const int no = eff_n(p.no_max, p.no_dev);             // real row count (device side): capacities run 1.5-2x above it
+  const int ntiles = (no + kBM - 1) / kBM;
   const int K = p.K;
-  const bool bres = Cfg::resident(K);
-  const int TPS = p.sc;                              // taps per slab (host: Cfg::tps)
-  const int SPT = (K + TPS - 1) / TPS;               // slabs per tile
-  const int NB = p.nb;                               // streamed-weight stages
+  const int NCHT = Cfg::num_chunks(K);               // chunks of a tile's K range
+  constexpr int NCH = Cfg::kSlabChunksMax;           // chunks per slab
+  const int SPT = (NCHT + NCH - 1) / NCH;            // slabs per tile
   const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const int total = my_tiles * SPT;                  // slabs of this CTA
 
   const uint32_t bars = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = bars + 1024u;
-  const uint32_t slab_wbytes = (uint32_t)(TPS * CIN / 64) * Cfg::kBBytes;   // streamed: weight bytes of a full slab
 
   if (tid == 0) {
     for (int s = 0; s < kSlots; ++s) {
-      mbar_init(bars + kBarFull + 8 * s, 4);           // the four warps of the slot's gather group
+      mbar_init(bars + kBarFull + 8 * s, kGatherWarps);
       mbar_init(bars + kBarEmpty + 8 * s, 1);          // tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -150,10 +116,6 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tr_kernel(ConvFwdArgs p) {
       mbar_init(bars + kBarAccEmpty + 8 * a, 4);
     }
     mbar_init(bars + kBarB, 1);
-    for (int s = 0; s < 8; ++s) {
-      mbar_init(bars + kBarBFull + 8 * s, 1);
-      mbar_init(bars + kBarBEmpty + 8 * s, 1);
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
@@ -176,85 +138,60 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tr_kernel(ConvFwdArgs p) {
     // timing experiment: set-up and tear-down only
   } else if (warp < kGatherWarps) {
     // ===================== gather: rulebook + rows -> registers -> TMEM =====================
-    const int q = warp & 3, g = warp >> 2;
-    const uint32_t t_slot = ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::kAccCols + g * Cfg::kSlotCols);
+    // Straight-line code: a slab always has NP pieces per thread (the slab size is a compile-time constant; pieces
+    // past the tile's K range read the zero row and land in columns no MMA reads), so the NP index loads, the NP row
+    // loads and the NP tcgen05.st of a slab are issued back to back with nothing but address arithmetic between them.
+    // (r2 A/B: a rotating window — store piece i of slab n, immediately request piece i of slab n+1 into the freed
+    // registers, indices two slabs ahead — keeps the same NP rows in flight and measured SLOWER, 27.1 vs 22.5 us on
+    // the 16x16 level-1 layer: the window cannot hold more than one slab, and ptxas moves the loads behind the stores.)
+    constexpr int NP = Cfg::kSlabChunksMax;           // pieces per thread per slab = chunks per slab
+    const int q = warp & 3, r = warp >> 2;            // row quarter, quarter of the slab's K range
     const char* in = reinterpret_cast<const char*>(p.in);
     const char* zrow = reinterpret_cast<const char*>(g_zero_row);
     const int ld = p.ld;
-    constexpr int TPSMAX = Cfg::kTpsMax, TB = Cfg::kBatch;
-    constexpr int LASTB0 = (TPSMAX - 1) / TB * TB;                // first tap of the last batch
-    const int AB = p.ablate;             // COMB_TS_ABLATE: timing experiments only (results are garbage)
-    const uint32_t bar_empty = bars + kBarEmpty + 8 * g, bar_full = bars + kBarFull + 8 * g;
-
-    // position of this group's current slab (ti, sl) and of the one whose indices are being fetched (nti, nsl):
-    // the group takes every fourth slab of the CTA's sequence, so the position advances by 4 slabs, no division
-    auto advance = [&](int& ti, int& sl) {
-      sl += kSlots;
-      while (sl >= SPT) {
-        sl -= SPT;
-        ++ti;
-      }
-    };
-    // indices of slab (ti, sl) for this thread's row: nbr[k0 + t][tile * 128 + row]; -1 = absent / past the end
-    int idx[TPSMAX];
+    // slab sl, this warp: global pieces (4 * sl + r) * NP + i; piece gp -> tap gp >> kLogPPT, channels 16 * (gp % kPPT)
+    int idx[NP];
     auto load_idx = [&](int ti, int sl) {
       const int row = ((int)blockIdx.x + ti * (int)gridDim.x) * kBM + q * 32 + lane;
-      const int k0 = sl * TPS;
-      const int nt = K - k0 < TPS ? K - k0 : TPS;
-      const int* src = p.nbr + (size_t)k0 * ld + row;
-      const bool live = row < no && ti < my_tiles && !(AB & 16);
+      const int gp0 = (4 * sl + r) * NP;
+      const bool live = row < no && ti < my_tiles;
+      const int* src = p.nbr + row;
 #pragma unroll
-      for (int t = 0; t < TPSMAX; ++t) {
-        idx[t] = -1;
-        if (t < nt && live) idx[t] = __ldg(src + (size_t)t * ld);
+      for (int i = 0; i < NP; ++i) {
+        const int tap = (gp0 + i) >> Cfg::kLogPPT;
+        idx[i] = -1;
+        if (tap < K && live) idx[i] = __ldg(src + (size_t)tap * ld);
       }
     };
-    if (AB & 256) {
-      // timing experiment: the bare hand-shake of a gather group
-      uint32_t use = 0;
-      for (int j = g; j < total; j += kSlots, ++use) {
-        mbar_wait(bar_empty, (use & 1u) ^ 1u);
-        if (lane == 0) mbar_arrive(bar_full);
+    int ti = 0, sl = 0;
+    load_idx(0, 0);
+    uint32_t j = 0;
+    const uint32_t t_base = ((uint32_t)(q * 32) << 16) + (uint32_t)Cfg::kAccCols + (uint32_t)(r * NP * 8);
+#pragma unroll 1
+    for (; ti < my_tiles; ++j) {
+      const uint32_t slot = j & 1u;
+      const int gp0 = (4 * sl + r) * NP;
+      uint32_t v[NP][8];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const int ch = (gp0 + i) & (Cfg::kPPT - 1);
+        const char* src = idx[i] >= 0 ? in + ((size_t)(uint32_t)idx[i] * (CIN * 2) + ch * 32) : zrow;
+        ldg256(src, v[i]);
       }
-    } else {
-      int ti = 0, sl = g;
-      while (sl >= SPT) {
-        sl -= SPT;
+      // next slab: its indices ride behind this slab's loads (past the end: all -1, no loads)
+      if (++sl == SPT) {
+        sl = 0;
         ++ti;
       }
-      int nti = ti, nsl = sl;
       load_idx(ti, sl);
-      uint32_t par = 1;                   // parity to wait for on the slot's empty barrier
-#pragma unroll 1
-      for (; ti < my_tiles; advance(ti, sl), par ^= 1u) {
-        const int k0 = sl * TPS;
-        const int nt = K - k0 < TPS ? K - k0 : TPS;       // taps of this slab
-        advance(nti, nsl);
+      mbar_wait_warp(bars + kBarEmpty + 8 * slot, ((j >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t t_dst = t_base + slot * Cfg::kSlotCols;
 #pragma unroll
-        for (int b0 = 0; b0 < TPSMAX; b0 += TB) {
-          uint32_t v[TB][Cfg::kTapRegs];
-#pragma unroll
-          for (int t = 0; t < TB; ++t) {
-            if (b0 + t < TPSMAX && b0 + t < nt && !(AB & 4)) {
-              const char* src = idx[b0 + t] >= 0 ? in + (size_t)(uint32_t)idx[b0 + t] * (CIN * 2) : zrow;
-#pragma unroll
-              for (int i = 0; i < CIN / 16; ++i) ldg256(src + 32 * i, *reinterpret_cast<uint32_t(*)[8]>(&v[t][8 * i]));
-            }
-          }
-          // the next slab's indices ride behind the last batch of loads of this one (past the end: all -1, no loads)
-          if (b0 == LASTB0) load_idx(nti, nsl);
-          if (b0 == 0) {
-            mbar_wait(bar_empty, par);
-            tc_fence_after();
-          }
-#pragma unroll
-          for (int t = 0; t < TB; ++t)
-            if (b0 + t < TPSMAX && b0 + t < nt && !(AB & 6)) tmem_st_row<Cfg::kTapRegs>(t_slot + (uint32_t)((b0 + t) * Cfg::kTapCols), v[t]);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        if (lane == 0) mbar_arrive(bar_full);
-      }
+      for (int i = 0; i < NP; ++i) tmem_st_x8(t_dst + 8 * i, v[i]);
+      tmem_st_wait();
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(bars + kBarFull + 8 * slot);
     }
   } else if (warp < kEpiWarp0 + 4) {
     // ===================== epilogue =====================
@@ -270,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tr_kernel(ConvFwdArgs p) {
         rv[0] = __ldg(rp);
         rv[1] = __ldg(rp + 1);
       }
-      mbar_wait_sleep(bars + kBarAccFull + 8 * a, (uint32_t)(ti >> 1) & 1u);
+      mbar_wait_sleep_warp(bars + kBarAccFull + 8 * a, (uint32_t)(ti >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = ((uint32_t)(q * 32) << 16) + a * COUT;
       if (!(p.ablate & 8))
@@ -337,81 +274,60 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tr_kernel(ConvFwdArgs p) {
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    // Everything this thread touches is derived from kernel parameters, blockIdx and constants (the tile count comes
-    // from the launch bound no_max, not from the device-side row count: a tile past the real end is multiplied like
-    // any other and simply not stored), so the whole loop lives in uniform registers.
+    // Addresses and descriptors are derived from kernel parameters, blockIdx and constants only, so they live in
+    // uniform registers; only the trip count (from the device-side row count) sits in an ordinary register.
     // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B, N>>3 [17,23), M>>4 [24,29)
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
     constexpr uint32_t kChunkStep = (uint32_t)Cfg::kBBytes >> 4;      // descriptor units between 64-wide K chunks
     const int AB = p.ablate;
     if (elect_one_sync()) {
-      if (bres) mbar_wait(bars + kBarB, 0);
-      uint32_t j = 0, bs = 0, bph = 0;
+      {
+        // the weight image: one bulk copy, resident for the life of the CTA
+        const uint32_t bytes = (uint32_t)NCHT * Cfg::kBBytes;
+        mbar_arrive_expect_tx(bars + kBarB, bytes);
+        bulk_copy_g2s(w_base, p.wpacked, bytes, bars + kBarB);
+        mbar_wait(bars + kBarB, 0);
+      }
+      uint32_t j = 0;
       const uint64_t desc0 = make_desc_sw128(w_base);
+      const uint64_t desc_hi = desc0 & 0xFFFFFFFF00000000ull;
+      bool ready = false;                  // the next slab's full barrier was seen complete by the look-ahead probe
 #pragma unroll 1
       for (int ti = 0; ti < my_tiles; ++ti) {
         const uint32_t a = (uint32_t)ti & 1u;
         if (!(AB & 128)) mbar_wait(bars + kBarAccEmpty + 8 * a, (((uint32_t)ti >> 1) & 1u) ^ 1u);
         const uint32_t tmem_d = a * COUT;
-        uint32_t dlo = (uint32_t)desc0, kk = 0, acc = 0;      // weight descriptor walks through the tile's K range
-        int k_left = K;
+        uint32_t dlo = (uint32_t)desc0, acc = 0;      // the weight descriptor walks through the tile's K range
+        int c_left = NCHT;
 #pragma unroll 1
         for (int sl = 0; sl < SPT; ++sl, ++j) {
-          const uint32_t slot = j & (kSlots - 1);
-          const int nt = k_left < TPS ? k_left : TPS;
-          k_left -= nt;
-          const int nsteps = nt * (CIN / 16);                       // K = 16 per MMA
-          if (!bres) {
-            mbar_wait(bars + kBarBFull + 8 * bs, bph);
-            dlo = (uint32_t)desc0 + bs * (slab_wbytes >> 4);
-            kk = 0;
-          }
-          mbar_wait(bars + kBarFull + 8 * slot, (j >> 2) & 1u);
+          const uint32_t slot = j & 1u;
+          const int nchs = c_left < NCH ? c_left : NCH;
+          c_left -= nchs;
+          if (!ready) mbar_wait(bars + kBarFull + 8 * slot, (j >> 1) & 1u);
           tc_fence_after();
           uint32_t tmem_a = (uint32_t)Cfg::kAccCols + slot * Cfg::kSlotCols;
+          // look-ahead: the probe's latency (~150 cycles) hides behind the MMAs issued below
+          const uint32_t j2 = j + 1;
+          ready = !(AB & 32) && mbar_test(bars + kBarFull + 8 * (j2 & 1u), (j2 >> 1) & 1u);
           if (!(AB & 1)) {
-#pragma unroll 4
-            for (int s = 0; s < nsteps; ++s) {
-              umma_bf16_ts(tmem_d, tmem_a, (desc0 & 0xFFFFFFFF00000000ull) | dlo, idesc, acc);
+#pragma unroll 1
+            for (int c = 0; c < nchs; ++c) {
+              umma_bf16_ts(tmem_d, tmem_a, desc_hi | dlo, idesc, acc);
+              umma_bf16_ts(tmem_d, tmem_a + 8, desc_hi | (dlo + 2), idesc, 1u);
+              umma_bf16_ts(tmem_d, tmem_a + 16, desc_hi | (dlo + 4), idesc, 1u);
+              umma_bf16_ts(tmem_d, tmem_a + 24, desc_hi | (dlo + 6), idesc, 1u);
               acc = 1;
-              tmem_a += 8;
-              dlo += 2;
-              if (++kk == 4) {
-                kk = 0;
-                dlo += kChunkStep - 8;
-              }
+              tmem_a += 32;
+              dlo += kChunkStep;
             }
           }
           umma_commit(bars + kBarEmpty + 8 * slot);
-          if (!bres) {
-            umma_commit(bars + kBarBEmpty + 8 * bs);
-            if (++bs == (uint32_t)NB) { bs = 0; bph ^= 1u; }
-          }
         }
         if (!(AB & 128)) umma_commit(bars + kBarAccFull + 8 * a);
       }
     }
     __syncwarp();
-  } else if (warp == kBWarp && lane == 0) {
-    // ===================== weights =====================
-    if (bres) {
-      const uint32_t bytes = (uint32_t)Cfg::num_chunks(K) * Cfg::kBBytes;
-      mbar_arrive_expect_tx(bars + kBarB, bytes);
-      bulk_copy_g2s(w_base, p.wpacked, bytes, bars + kBarB);
-    } else {
-      const int nchunks = Cfg::num_chunks(K), cps = TPS * CIN / 64;      // chunks per full slab
-      int bs = 0;
-      uint32_t bph = 0;
-      for (int ti = 0; ti < my_tiles; ++ti)
-        for (int sl = 0; sl < SPT; ++sl) {
-          const int c0 = sl * cps;
-          const uint32_t bytes = (uint32_t)(nchunks - c0 < cps ? nchunks - c0 : cps) * Cfg::kBBytes;
-          mbar_wait(bars + kBarBEmpty + 8 * bs, bph ^ 1u);
-          mbar_arrive_expect_tx(bars + kBarBFull + 8 * bs, bytes);
-          bulk_copy_g2s(w_base + (uint32_t)bs * slab_wbytes, p.wpacked + (size_t)c0 * Cfg::kBBytes, bytes, bars + kBarBFull + 8 * bs);
-          if (++bs == NB) { bs = 0; bph ^= 1u; }
-        }
-    }
   }
 
   tc_fence_before();
@@ -426,27 +342,16 @@ template <int CIN, int COUT>
 int launch_tr(const ConvFwdArgs& p_in, cudaStream_t stream) {
   using Cfg = TrCfg<CIN, COUT>;
   ConvFwdArgs p = p_in;
-  const bool bres = Cfg::resident(p.K);
-  p.sc = Cfg::tps(p.K, bres);
+  if (!Cfg::resident(p.K)) {
+    set_error("comb_spconv_fwd_bf16: the row-per-thread kernel keeps the weight image in shared memory; %d x %d x %d does not fit", p.K, CIN, COUT);
+    return COMB_EINVAL;
+  }
+  p.sc = Cfg::kSlabChunksMax;        // chunks per slab: fixed, the last slab of a tile may be partly padding
   {
     const char* ab = getenv("COMB_TS_ABLATE");     // read per launch: timing experiments flip it inside one process
     p.ablate = ab ? atoi(ab) : 0;
   }
-  size_t smem = 2048;
-  if (bres) {
-    smem += (size_t)Cfg::num_chunks(p.K) * Cfg::kBBytes;
-    p.nb = 0;
-  } else {
-    const size_t stage = (size_t)(p.sc * CIN / 64) * Cfg::kBBytes;
-    int nb = (int)((kSmemMax - 2048) / stage);
-    if (nb > kMaxBStages) nb = kMaxBStages;
-    if (nb < 2 || p.sc < 1) {
-      set_error("comb_spconv_fwd_bf16: weight stage of %zu bytes does not fit twice in shared memory", stage);
-      return COMB_EINVAL;
-    }
-    p.nb = nb;
-    smem += (size_t)nb * stage;
-  }
+  const size_t smem = 2048 + (size_t)Cfg::num_chunks(p.K) * Cfg::kBBytes;
   static thread_local DevOnce configured;   // per device: the attribute is a per-device property
   if (configured.first())
     COMB_CUDA(cudaFuncSetAttribute(spconv_tr_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
@@ -470,6 +375,11 @@ int dispatch_cout(int Cout, const ConvFwdArgs& p, cudaStream_t stream) {
 }
 
 }  // namespace
+
+bool tr_supported(int Cin_p, int Cout, int K) {
+  const long long chunks = Cin_p <= 64 ? ((long long)K * Cin_p + 63) / 64 : (long long)K * (Cin_p / 64);
+  return chunks * Cout * 128 + 2048 <= kSmemMax;
+}
 
 int tr_fwd_bf16(const ConvFwdArgs& p, int Cin_p, int Cout, cudaStream_t stream) {
   switch (Cin_p) {

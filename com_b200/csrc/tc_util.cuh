@@ -38,6 +38,19 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
         : "memory");
   }
 }
+// Whole-warp wait with ONE polling lane.  The barrier unit serves try_wait per thread, not per warp (r2
+// scripts/micro/mbar_bench.cu: 32 lanes polling a completed phase cost 41 cycles per round, and a CTA with 16 waiting
+// warps keeps 512 polls in flight: with nothing but its hand-shakes left, the 16-warp gather of the sparse-conv kernels
+// ran at ~1500 cycles per barrier round).  Lane 0 polls, __syncwarp releases the others (and orders their later
+// accesses after lane 0's acquire).
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void mbar_wait_sleep_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait_sleep(bar, parity);
+  __syncwarp();
+}
 // non-blocking probe of a phase (acquire on success)
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t done;

@@ -17,7 +17,7 @@ if __name__ == "__main__":
             nbr = torch.stack([(o + k - 13).clamp(0, n - 1) for k in range(27)]).contiguous()
             x = torch.randn((n, cin), device="cuda").to(torch.bfloat16)
             res = {}
-            for m in (0, 29, 29 + 128, 29 + 256, 29 + 128 + 256, 64):
+            for m in (0, 1, 4 | 16, 29, 64):
                 os.environ["COMB_TS_ABLATE"] = str(m)
                 res[m] = round(timed(lambda: ops.spconv_fwd_bf16(x, w, 27, cout, nbr)), 1)
             os.environ["COMB_TS_ABLATE"] = "0"
