@@ -61,6 +61,53 @@ def _hook_center_head(mod):
         generate_predicted_boxes._comb = True
         generate_predicted_boxes.reference = reference_method
         cls.generate_predicted_boxes = generate_predicted_boxes
+    _hook_center_targets(mod)
+
+
+def _hook_center_targets(mod):
+    """curriculum_center_head.py:203-296, 431-473: target assignment and the curriculum groups on the device
+    (comb_centerhead_assign_targets / comb_centerhead_cluster_groups) for single-head configurations."""
+    from .pcdet_ops import center_targets
+    cls = getattr(mod, "CurriculumCenterHead", None)
+    if cls is None or getattr(cls.assign_targets, "_comb", False):
+        return
+    ref_assign, ref_cluster = cls.assign_targets, cls.cluster
+
+    def assign_targets(self, gt_boxes, feature_map_size=None, npgt=None, true_object=None, _ref=ref_assign, **kwargs):
+        if center_targets.supported_head(self, gt_boxes):
+            return center_targets.assign_targets(self, gt_boxes, feature_map_size=feature_map_size, npgt=npgt,
+                                                 true_object=true_object, **kwargs)
+        return _ref(self, gt_boxes, feature_map_size=feature_map_size, npgt=npgt, true_object=true_object, **kwargs)
+
+    def cluster(self, gt_boxes, true_object, occupancy_ratio, facade_type, _ref=ref_cluster):
+        if center_targets.supported_head(self, gt_boxes) and true_object is not None:
+            return center_targets.cluster(self, gt_boxes, true_object, occupancy_ratio, facade_type)
+        return _ref(self, gt_boxes, true_object, occupancy_ratio, facade_type)
+
+    for new, ref in ((assign_targets, ref_assign), (cluster, ref_cluster)):
+        new._comb = True
+        new.reference = ref
+    cls.assign_targets = assign_targets
+    cls.cluster = cluster
+
+
+def _hook_loss_utils(mod):
+    """pcdet/utils/loss_utils.py:1180-1309: the object loop and the group confidences of the COM focal loss on the
+    device (comb_comloss_reweight / comb_comloss_group_confidence)."""
+    from .pcdet_ops import center_targets
+    cls = getattr(mod, "FocalLossCenterCurriculum", None)
+    if cls is None or getattr(cls.neg_loss, "_comb", False):
+        return
+    reference_method = cls.neg_loss
+
+    def neg_loss(self, pred, gt, radius_map, box_mask, mask=None, epoch=None, _ref=reference_method):
+        if center_targets.supported_loss(self, pred, radius_map, mask):
+            return center_targets.neg_loss(self, pred, gt, radius_map, box_mask, mask=mask, epoch=epoch)
+        return _ref(self, pred, gt, radius_map, box_mask, mask=mask, epoch=epoch)
+
+    neg_loss._comb = True
+    neg_loss.reference = reference_method
+    cls.neg_loss = neg_loss
 
 
 POST_IMPORT_HOOKS = {
@@ -68,6 +115,7 @@ POST_IMPORT_HOOKS = {
     "pcdet.utils.box_utils": _hook_box_utils,
     "pcdet.models.dense_heads.center_head": _hook_center_head,
     "pcdet.models.dense_heads.curriculum_center_head": _hook_center_head,
+    "pcdet.utils.loss_utils": _hook_loss_utils,
 }
 
 

@@ -5,7 +5,7 @@ without a GPU); if it cannot be loaded, or a call fails, a RuntimeError is raise
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_double, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcomb200.so")
@@ -81,6 +81,13 @@ SIGNATURES = {
     "comb_centerhead_decode_nms": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
                                            c_float, c_float, _PF, c_float, _P, c_float, c_int, c_int, _P, _P, _P, _P, _P,
                                            c_size_t, _P]),
+    "comb_centerhead_assign_targets": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float,
+                                               c_float, c_int, c_int, c_int, c_double, c_int, c_int, c_float, _P, _P, c_int,
+                                               c_int, _P, _P, _P, _P, _P, c_int, _P]),
+    "comb_centerhead_cluster_groups": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P]),
+    "comb_comloss_group_confidence": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "comb_comloss_reweight": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_double, c_double, c_double,
+                                      c_double, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
 }
 
 

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libcomb200.so")
-SOURCES = ["api.cu", "voxelize.cu", "rulebook.cu", "gridindex.cu", "conv_f32.cu", "conv_tc.cu", "conv_ts.cu", "conv_tr.cu", "conv_wgrad.cu", "elementwise.cu", "bn.cu", "boxes.cu", "decode.cu"]
+SOURCES = ["api.cu", "voxelize.cu", "rulebook.cu", "gridindex.cu", "conv_f32.cu", "conv_tc.cu", "conv_ts.cu", "conv_tr.cu", "conv_wgrad.cu", "elementwise.cu", "bn.cu", "boxes.cu", "decode.cu", "targets.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -17,7 +17,7 @@ __all__ = [
     "voxelize", "mean_vfe", "hash_build", "conv_out_coords", "conv_out_shape", "nbrmap_build",
     "nbrmap_transpose", "nbrmap_to_pairs", "spconv_fwd_f32", "spconv_dgrad_f32", "spconv_wgrad_f32", "spconv_wgrad_bf16",
     "pack_weight_bf16", "spconv_fwd_bf16", "affine_relu", "cast_pad", "bn_train_fwd", "bn_train_bwd", "col_sum", "dense", "dense_gather", "DenseFunction", "points_in_boxes_mask",
-    "points_in_any_box", "points_in_boxes_index", "boxes_bev", "nms", "centerhead_decode_nms", "box_trig_host", "box_trig4_host",
+    "points_in_any_box", "points_in_boxes_index", "boxes_bev", "nms", "centerhead_decode_nms", "centerhead_assign_targets", "centerhead_cluster_groups", "comloss_group_confidence", "comloss_reweight", "box_trig_host", "box_trig4_host",
 ]
 
 
@@ -712,3 +712,114 @@ def centerhead_decode_nms(hm, center, center_z, dim, rot, K, feature_map_stride,
             float(score_thresh), _p(label_map), float(nms_thresh), int(nms_pre_max), int(nms_post_max), _p(boxes),
             _p(scores), _p(labels), _p(counts), _p(ws), nbytes, _stream()), "comb_centerhead_decode_nms")
     return boxes, scores, labels, counts
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# f1 — CenterHead target assignment / COM loss re-weighting (targets.cu)
+_GTAB_RMAX = 48
+_gtab_cache = {}
+
+
+def _gaussian_tables(device):
+    """Gaussian windows of radius 0.._GTAB_RMAX, built with the formula of centernet_utils.gaussian2D
+    (pcdet/models/model_utils/centernet_utils.py:78-84: float64 exp, eps cut, cast to fp32) so that the device heat maps
+    carry the reference's values bit for bit."""
+    key = str(device)
+    if key not in _gtab_cache:
+        import numpy as np
+        tabs, offs, o = [], [], 0
+        for r in range(_GTAB_RMAX + 1):
+            d = 2 * r + 1
+            m = n = (d - 1.) / 2.
+            y, x = np.ogrid[-m:m + 1, -n:n + 1]
+            sigma = d / 6
+            h = np.exp(-(x * x + y * y) / (2 * sigma * sigma))
+            h[h < np.finfo(h.dtype).eps * h.max()] = 0
+            tabs.append(torch.from_numpy(h).float().reshape(-1))
+            offs.append(o)
+            o += d * d
+        offs.append(o)
+        _gtab_cache[key] = (torch.cat(tabs).to(device), torch.tensor(offs, dtype=torch.int32, device=device))
+    return _gtab_cache[key]
+
+
+def centerhead_assign_targets(gt_boxes, npgt, group, cls_map, num_classes_head, feature_map_size, feature_map_stride,
+                              point_cloud_range, voxel_size, num_max_objs=500, gaussian_overlap=0.1, min_radius=2,
+                              filter_points=False, min_points=1):
+    """assign_target_of_single_head for every frame of ONE separate head (comb_centerhead_assign_targets).
+    gt_boxes (B,M,C) fp32 cuda, npgt (B,M), group (B,M) int64 or None, cls_map (n_cls+1,) int32: global class id ->
+    index inside the head or -1; feature_map_size = (W, H).
+    -> heatmap (B,Ch,H,W), ret_boxes (B,N,C), inds (B,N) int64, mask (B,N) fp32, radius_map (B,N,4|5) int64."""
+    lib = _lib.load()
+    _need(gt_boxes, torch.float32, "gt_boxes")
+    _need(cls_map, torch.int32, "cls_map")
+    B, M, C = [int(v) for v in gt_boxes.shape]
+    dev = gt_boxes.device
+    npgt = npgt.to(device=dev, dtype=torch.float32).contiguous()
+    if group is not None:
+        group = group.to(device=dev, dtype=torch.int64).contiguous()
+    W, H = int(feature_map_size[0]), int(feature_map_size[1])
+    R = 5 if group is not None else 4
+    N = int(num_max_objs)
+    heatmap = torch.zeros((B, num_classes_head, H, W), dtype=torch.float32, device=dev)
+    ret_boxes = torch.zeros((B, N, C), dtype=torch.float32, device=dev)
+    inds = torch.zeros((B, N), dtype=torch.int64, device=dev)
+    mask = torch.zeros((B, N), dtype=torch.float32, device=dev)
+    radius_map = torch.zeros((B, N, R), dtype=torch.int64, device=dev)
+    gtab, goff = _gaussian_tables(dev)
+    import numpy as np
+    f32 = lambda v: float(np.float32(v))
+    with _Scope("centerhead_assign_targets", B=B, M=M):
+        check(lib.comb_centerhead_assign_targets(
+            _p(gt_boxes), _p(npgt), _p(group), _p(cls_map), int(cls_map.numel()) - 1, B, M, C, f32(point_cloud_range[0]),
+            f32(point_cloud_range[1]), f32(voxel_size[0]), f32(voxel_size[1]), f32(feature_map_stride), W, H, N,
+            float(gaussian_overlap), int(min_radius), 1 if filter_points else 0, float(min_points), _p(gtab), _p(goff),
+            _GTAB_RMAX, int(num_classes_head), _p(heatmap), _p(ret_boxes), _p(inds), _p(mask), _p(radius_map), R, _stream()),
+            "comb_centerhead_assign_targets")
+    return heatmap, ret_boxes, inds, mask, radius_map
+
+
+def centerhead_cluster_groups(gt_boxes, true_object, occupancy_ratio, facade_type):
+    """CurriculumCenterHead.cluster on the device -> group (B,M) int64."""
+    lib = _lib.load()
+    _need(gt_boxes, torch.float32, "gt_boxes")
+    B, M, C = [int(v) for v in gt_boxes.shape]
+    dev = gt_boxes.device
+    conv = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+    to, oc, fa = conv(true_object), conv(occupancy_ratio), conv(facade_type)
+    group = torch.empty((B, M), dtype=torch.int64, device=dev)
+    check(lib.comb_centerhead_cluster_groups(_p(gt_boxes), B * M, C, _p(to), _p(oc), _p(fa), _p(group), _stream()),
+          "comb_centerhead_cluster_groups")
+    return group
+
+
+def comloss_group_confidence(pred, radius_map, n_class, n_group):
+    """FocalLossCenterCurriculum.confidence_of_all_groups -> (confidence_all, num_all), both (n_class, n_group) fp32."""
+    lib = _lib.load()
+    _need(pred, torch.float32, "pred")
+    _need(radius_map, torch.int64, "radius_map")
+    B, Ch, H, W = [int(v) for v in pred.shape]
+    nobj, R = int(radius_map.shape[1]), int(radius_map.shape[2])
+    conf = torch.empty((n_class, n_group), dtype=torch.float32, device=pred.device)
+    num = torch.empty((n_class, n_group), dtype=torch.float32, device=pred.device)
+    check(lib.comb_comloss_group_confidence(_p(pred), B, Ch, H, W, _p(radius_map), nobj, R, int(n_class), int(n_group),
+                                            _p(conf), _p(num), _stream()), "comb_comloss_group_confidence")
+    return conf, num
+
+
+def comloss_reweight(pred, radius_map, box_mask, mask, threshold, elongation, height, K=1.0, mode=0, fixed_radius=0,
+                     add_radius=0, only_center=False, active=True):
+    """The object loop of FocalLossCenterCurriculum.neg_loss: box_mask (B,N) and mask (B,Ch,H,W) are updated IN PLACE."""
+    lib = _lib.load()
+    _need(pred, torch.float32, "pred")
+    _need(radius_map, torch.int64, "radius_map")
+    _need(box_mask, torch.float32, "box_mask")
+    _need(mask, torch.float32, "mask")
+    B, Ch, H, W = [int(v) for v in pred.shape]
+    nobj, R = int(radius_map.shape[1]), int(radius_map.shape[2])
+    with _Scope("comloss_reweight", B=B, N=nobj):
+        check(lib.comb_comloss_reweight(_p(pred), B, Ch, H, W, _p(radius_map), nobj, R, float(threshold), float(elongation),
+                                        float(height), float(K), int(mode), int(fixed_radius), int(add_radius),
+                                        1 if only_center else 0, 1 if active else 0, _p(box_mask), _p(mask), _stream()),
+              "comb_comloss_reweight")
+    return box_mask, mask

@@ -338,6 +338,42 @@ int comb_centerhead_decode_nms(const float* hm, const float* center, const float
                                float* out_scores, int* out_labels, int* out_counts, void* workspace,
                                size_t workspace_bytes, void* stream);
 
+/* ---- f1: CenterHead target assignment and the COM loss re-weighting -------------------------------------------------
+ * Replaces the per-object Python loops of CurriculumCenterHead (pcdet/models/dense_heads/curriculum_center_head.py):
+ * cluster (:431-473), assign_targets / assign_target_of_single_head (:120-296; CenterHead.assign_targets,
+ * center_head.py:119-236, is the same without the point-count filter and the group column) with
+ * centernet_utils.gaussian_radius / draw_gaussian_to_heatmap (pcdet/models/model_utils/centernet_utils.py:48-108), and
+ * of FocalLossCenterCurriculum (pcdet/utils/loss_utils.py): confidence_of_all_groups (:1131-1178) and the object loop
+ * of neg_loss (:1222-1287) with centernet_utils.draw_mask_to_heatmap (:110-131).  All pointers are device pointers.
+ *
+ * comb_centerhead_assign_targets: ONE separate head, all frames.  gt_boxes [B,M,C] fp32 (C >= 8, class id 1-based in
+ *   the last column, 0 = padding), npgt [B,M] fp32, group [B,M] int64 or NULL (R = 5 needs it), cls_map [n_cls+1]
+ *   int32: global class id -> index inside this head or -1.  x0,y0 = POINT_CLOUD_RANGE[0:2], vx,vy = VOXEL_SIZE[0:2],
+ *   stride = FEATURE_MAP_STRIDE, (W,H) = feature map, overlap = GAUSSIAN_OVERLAP, filter_points = (epoch <=
+ *   EPOCH_THRED), gtab / gtab_off / rmax: Gaussian windows of radius 0..rmax built on the host with the reference's
+ *   numpy formula (gtab_off[r] = offset of the (2r+1)^2 window).  Outputs must be ZERO-filled by the caller:
+ *   heatmap [B,Ch,H,W], ret_boxes [B,max_objs,C], inds [B,max_objs] int64, mask [B,max_objs] fp32, radius_map
+ *   [B,max_objs,R] int64 (class, x, y, radius[, group]). */
+int comb_centerhead_assign_targets(const float* gt_boxes, const float* npgt, const long long* group,
+                                   const int* cls_map, int n_cls, int B, int M, int C, float x0, float y0, float vx,
+                                   float vy, float stride, int W, int H, int max_objs, double overlap, int min_radius,
+                                   int filter_points, float min_points, const float* gtab, const int* gtab_off,
+                                   int rmax, int Ch, float* heatmap, float* ret_boxes, long long* inds, float* mask,
+                                   long long* radius_map, int R, void* stream);
+/* cluster(): curriculum group of each of n ground-truth boxes (gt_boxes [n,C]); the three attribute arrays are fp32. */
+int comb_centerhead_cluster_groups(const float* gt_boxes, int n, int C, const float* true_object,
+                                   const float* occupancy_ratio, const float* facade_type, long long* group,
+                                   void* stream);
+/* confidence_of_all_groups(): conf / num [n_class, n_group] fp32 from pred [B,Ch,H,W] and radius_map [B,nobj,R]. */
+int comb_comloss_group_confidence(const float* pred, int B, int Ch, int H, int W, const long long* radius_map, int nobj,
+                                  int R, int n_class, int n_group, float* conf, float* num, void* stream);
+/* The object loop of neg_loss(): per object weight from the predicted confidence at its centre (mode 0: height / (1 +
+ * exp(elongation (c - threshold))) + 1 - height / 2; 1: K (c - threshold) + 1; 2: 1), written to box_mask [B,nobj]
+ * and drawn (assignment, object order) into mask [B,Ch,H,W]; active = (START <= epoch <= END). */
+int comb_comloss_reweight(const float* pred, int B, int Ch, int H, int W, const long long* radius_map, int nobj, int R,
+                          double threshold, double elongation, double height, double K, int mode, int fixed_radius,
+                          int add_radius, int only_center, int active, float* box_mask, float* mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,8 +129,11 @@ def main():
 
     out = {"workload": "configs[2] full step: reference CenterPoint + CurriculumCenterHead_x5 + COMLoss on the drop-ins, "
                        "batch 2 Waymo-shaped frames, fwd + bwd + AdamW", "modules": [type(m).__name__ for m in model.module_list]}
-    for label, env in (("fused_train_step", "1"), ("module_path", "0")):
+    # fused_train_step: everything on; reference_head_loops: the reference's own Python target assignment / COM loss loops
+    # (COMB_FUSED_TARGETS=0) on the fused backbone; module_path: additionally the per-module backbone
+    for label, env, tgt in (("fused_train_step", "1", "1"), ("reference_head_loops", "1", "0"), ("module_path", "0", "0")):
         os.environ["COMB_FUSED_TRAIN"] = env
+        os.environ["COMB_FUSED_TARGETS"] = tgt
         for _ in range(3):
             loss = step()
         torch.cuda.synchronize()
@@ -145,6 +148,7 @@ def main():
             step(timed=True)
         out[label]["breakdown_ms"] = {k: round(v / 5, 3) for k, v in stages.items()}
     os.environ.pop("COMB_FUSED_TRAIN", None)
+    os.environ.pop("COMB_FUSED_TARGETS", None)
     # eval: forward + fused post-processing
     model.eval()
     with torch.no_grad():
