@@ -110,12 +110,59 @@ def _hook_loss_utils(mod):
     cls.neg_loss = neg_loss
 
 
+def _hook_height_compression(mod):
+    """pcdet/models/backbones_2d/map_to_bev/height_compression.py:9-26 — with com_b200.sparse.config.bev == "bf16" the BEV
+    image is produced directly as channels-last bf16 (f4); otherwise the reference method runs unchanged."""
+    cls = getattr(mod, "HeightCompression", None)
+    if cls is None or getattr(cls.forward, "_comb", False):
+        return
+    reference_method = cls.forward
+
+    def forward(self, batch_dict, _ref=reference_method):
+        from .sparse import config
+        t = batch_dict["encoded_spconv_tensor"]
+        if config.bev != "bf16" or not hasattr(t, "dense_bev_bf16"):
+            return _ref(self, batch_dict)
+        batch_dict["spatial_features"] = t.dense_bev_bf16()
+        batch_dict["spatial_features_stride"] = batch_dict["encoded_spconv_tensor_stride"]
+        return batch_dict
+
+    forward._comb = True
+    forward.reference = reference_method
+    cls.forward = forward
+
+
+def _hook_bev_backbone(mod):
+    """pcdet/models/backbones_2d/base_bev_backbone.py:81-112 — a bf16 channels-last input (f4) runs the unchanged forward
+    under bf16 autocast; `spatial_features_2d` is handed on as fp32 (the dense head keeps its fp32 weights)."""
+    import torch
+    cls = getattr(mod, "BaseBEVBackbone", None)
+    if cls is None or getattr(cls.forward, "_comb", False):
+        return
+    reference_method = cls.forward
+
+    def forward(self, data_dict, _ref=reference_method):
+        x = data_dict["spatial_features"]
+        if x.dtype != torch.bfloat16:
+            return _ref(self, data_dict)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            data_dict = _ref(self, data_dict)
+        data_dict["spatial_features_2d"] = data_dict["spatial_features_2d"].float()
+        return data_dict
+
+    forward._comb = True
+    forward.reference = reference_method
+    cls.forward = forward
+
+
 POST_IMPORT_HOOKS = {
     "pcdet.models.backbones_3d.spconv_backbone": _hook_spconv_backbone,
     "pcdet.utils.box_utils": _hook_box_utils,
     "pcdet.models.dense_heads.center_head": _hook_center_head,
     "pcdet.models.dense_heads.curriculum_center_head": _hook_center_head,
     "pcdet.utils.loss_utils": _hook_loss_utils,
+    "pcdet.models.backbones_2d.map_to_bev.height_compression": _hook_height_compression,
+    "pcdet.models.backbones_2d.base_bev_backbone": _hook_bev_backbone,
 }
 
 

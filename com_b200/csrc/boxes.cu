@@ -702,3 +702,55 @@ extern "C" int comb_nms(const float* boxes, const float* trig, int n, float thre
                         long long* keep, int* num_keep, void* workspace, size_t workspace_bytes, void* stream_) {
   return comb_nms_dev(boxes, trig, n, nullptr, thresh, rotated, flavour, keep, num_keep, workspace, workspace_bytes, stream_);
 }
+
+// ---- f3: COMAug placement test -------------------------------------------------------------------------------------
+// valid[i] = (max_j iou1[i][j] + max_j iou2[i][j], diagonal of iou2 zeroed) == 0 — the collision test of the COMAug
+// database sampler (pcdet/datasets/augmentor/database_sampler_v2.py:600-604) — computed from the two IoU matrices
+// where they lie on the device: one byte per sampled box goes back to the host instead of S x (E + S) floats.
+// numpy's max propagates NaN (a degenerate box): NaN + x == 0 is false, the box is rejected as there.
+namespace comb {
+namespace {
+__global__ void __launch_bounds__(128) comaug_valid_kernel(const float* __restrict__ iou1, const float* __restrict__ iou2,
+                                                            int S, int E, unsigned char* __restrict__ valid) {
+  const int i = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float s_m1[4], s_m2[4];
+  __shared__ int s_nan[4];
+  float m1 = 0.0f, m2 = 0.0f;         // IoU >= 0, and a row of iou2 always holds its zeroed diagonal
+  int nan = 0;
+  for (int j = threadIdx.x; j < E; j += blockDim.x) {
+    const float v = iou1[(size_t)i * E + j];
+    nan |= (v != v);
+    m1 = fmaxf(m1, v);
+  }
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    const float v = j == i ? 0.0f : iou2[(size_t)i * S + j];
+    nan |= (v != v);
+    m2 = fmaxf(m2, v);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, d));
+    m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, d));
+    nan |= __shfl_xor_sync(0xffffffffu, nan, d);
+  }
+  if (lane == 0) { s_m1[warp] = m1; s_m2[warp] = m2; s_nan[warp] = nan; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 4; ++w) { m1 = fmaxf(m1, s_m1[w]); m2 = fmaxf(m2, s_m2[w]); nan |= s_nan[w]; }
+    if (E == 0) m1 = m2;              // `iou1 = iou1 if iou1.shape[1] > 0 else iou2`
+    valid[i] = (!nan && (m1 + m2) == 0.0f) ? 1 : 0;
+  }
+}
+}  // namespace
+}  // namespace comb
+
+extern "C" int comb_comaug_valid_mask(const float* iou1, const float* iou2, int S, int E, unsigned char* valid,
+                                      void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(S >= 0 && E >= 0, "comb_comaug_valid_mask: negative size");
+  if (S == 0) return COMB_OK;
+  COMB_CHECK_ARG((iou1 || E == 0) && iou2 && valid, "comb_comaug_valid_mask: null pointer");
+  comb::comaug_valid_kernel<<<S, 128, 0, stream>>>(iou1, iou2, S, E, valid);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}

@@ -368,3 +368,91 @@ extern "C" int comb_dense_gather(const float* dense, const int* coords, int n_ma
   COMB_LAUNCH_CHECK();
   return COMB_OK;
 }
+
+// ---- f4: the BEV tensor in channels-last bf16 -------------------------------------------------------------------------
+// HeightCompression (pcdet/models/backbones_2d/map_to_bev/height_compression.py:21-24) turns the encoded sparse tensor
+// into (N, C*D, H, W) for the 2D backbone (pcdet/models/backbones_2d/base_bev_backbone.py:81-112), channel index
+// c*D + z.  Here the rows are scattered straight into the NHWC image out[b][y][x][c*D + z] in bf16 (pre-zeroed by the
+// caller): the 2D backbone then runs its convolutions on bf16 tensor cores without a layout or dtype conversion pass,
+// and the image is half the bytes of the fp32 NCDHW one.  One warp per row, lanes walk the channels.
+namespace comb {
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) dense_scatter_nhwc_kernel(const T* __restrict__ feats, const int4* __restrict__ coords,
+                                                                  int n_max, const int* __restrict__ n_dev, int batch, int C,
+                                                                  int D, int H, int W, __nv_bfloat16* __restrict__ out) {
+  const int n = eff_n(n_max, n_dev);
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < n; row += gridDim.x * wpb) {
+    const int4 c = __ldg(coords + row);
+    if ((unsigned)c.x >= (unsigned)batch || (unsigned)c.y >= (unsigned)D || (unsigned)c.z >= (unsigned)H ||
+        (unsigned)c.w >= (unsigned)W)
+      continue;
+    __nv_bfloat16* o = out + (((size_t)c.x * H + c.z) * W + c.w) * ((size_t)C * D) + c.y;
+    for (int ch = lane; ch < C; ch += 32) o[(size_t)ch * D] = (__nv_bfloat16)feats[(size_t)row * C + ch];
+  }
+}
+// adjoint: rows[row][ch] = grad[b][y][x][ch*D + z]
+template <typename G, typename T>
+__global__ void __launch_bounds__(256) dense_gather_nhwc_kernel(const G* __restrict__ grad, const int4* __restrict__ coords,
+                                                                 int n_max, const int* __restrict__ n_dev, int batch, int C,
+                                                                 int D, int H, int W, T* __restrict__ out) {
+  const int n = eff_n(n_max, n_dev);
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < n; row += gridDim.x * wpb) {
+    const int4 c = __ldg(coords + row);
+    const bool ok = (unsigned)c.x < (unsigned)batch && (unsigned)c.y < (unsigned)D && (unsigned)c.z < (unsigned)H &&
+                    (unsigned)c.w < (unsigned)W;
+    const G* g = grad + (((size_t)(ok ? c.x : 0) * H + (ok ? c.z : 0)) * W + (ok ? c.w : 0)) * ((size_t)C * D) + (ok ? c.y : 0);
+    for (int ch = lane; ch < C; ch += 32) out[(size_t)row * C + ch] = (T)(ok ? (float)g[(size_t)ch * D] : 0.0f);
+  }
+}
+}  // namespace
+}  // namespace comb
+
+extern "C" int comb_dense_scatter_nhwc_bf16(const void* feats, int dtype, const int* coords, int n_max, const int* n_dev,
+                                            int batch, int C, int D, int H, int W, void* out, void* stream_) {
+  using namespace comb;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(batch >= 1 && C >= 1 && D >= 1 && H >= 1 && W >= 1 && n_max >= 0, "comb_dense_scatter_nhwc_bf16: bad shape");
+  if (n_max == 0) return COMB_OK;
+  COMB_CHECK_ARG(feats && coords && out, "comb_dense_scatter_nhwc_bf16: null pointer");
+  int blocks = cdiv(n_max, 8);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == COMB_DT_F32)
+    dense_scatter_nhwc_kernel<float><<<blocks, 256, 0, stream>>>((const float*)feats, (const int4*)coords, n_max, n_dev, batch,
+                                                                  C, D, H, W, (__nv_bfloat16*)out);
+  else if (dtype == COMB_DT_BF16)
+    dense_scatter_nhwc_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)feats, (const int4*)coords, n_max,
+                                                                          n_dev, batch, C, D, H, W, (__nv_bfloat16*)out);
+  else
+    COMB_CHECK_ARG(false, "comb_dense_scatter_nhwc_bf16: unknown dtype %d", dtype);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}
+
+extern "C" int comb_dense_gather_nhwc(const void* grad, int grad_dtype, const int* coords, int n_max, const int* n_dev,
+                                      int batch, int C, int D, int H, int W, void* out, int dtype, void* stream_) {
+  using namespace comb;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  COMB_CHECK_ARG(batch >= 1 && C >= 1 && D >= 1 && H >= 1 && W >= 1 && n_max >= 0, "comb_dense_gather_nhwc: bad shape");
+  if (n_max == 0) return COMB_OK;
+  COMB_CHECK_ARG(grad && coords && out, "comb_dense_gather_nhwc: null pointer");
+  COMB_CHECK_ARG((grad_dtype == COMB_DT_F32 || grad_dtype == COMB_DT_BF16) && (dtype == COMB_DT_F32 || dtype == COMB_DT_BF16),
+                 "comb_dense_gather_nhwc: unknown dtype");
+  int blocks = cdiv(n_max, 8);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const int4* cd = (const int4*)coords;
+  if (grad_dtype == COMB_DT_BF16 && dtype == COMB_DT_BF16)
+    dense_gather_nhwc_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)grad, cd, n_max, n_dev, batch, C, D, H, W, (__nv_bfloat16*)out);
+  else if (grad_dtype == COMB_DT_BF16)
+    dense_gather_nhwc_kernel<__nv_bfloat16, float><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)grad, cd, n_max, n_dev, batch, C, D, H, W, (float*)out);
+  else if (dtype == COMB_DT_BF16)
+    dense_gather_nhwc_kernel<float, __nv_bfloat16><<<blocks, 256, 0, stream>>>((const float*)grad, cd, n_max, n_dev, batch, C, D, H, W, (__nv_bfloat16*)out);
+  else
+    dense_gather_nhwc_kernel<float, float><<<blocks, 256, 0, stream>>>((const float*)grad, cd, n_max, n_dev, batch, C, D, H, W, (float*)out);
+  COMB_LAUNCH_CHECK();
+  return COMB_OK;
+}

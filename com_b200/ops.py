@@ -17,7 +17,7 @@ __all__ = [
     "voxelize", "mean_vfe", "hash_build", "conv_out_coords", "conv_out_shape", "nbrmap_build",
     "nbrmap_transpose", "nbrmap_to_pairs", "spconv_fwd_f32", "spconv_dgrad_f32", "spconv_wgrad_f32", "spconv_wgrad_bf16",
     "pack_weight_bf16", "spconv_fwd_bf16", "affine_relu", "cast_pad", "bn_train_fwd", "bn_train_bwd", "col_sum", "dense", "dense_gather", "DenseFunction", "points_in_boxes_mask",
-    "points_in_any_box", "points_in_boxes_index", "boxes_bev", "nms", "centerhead_decode_nms", "centerhead_assign_targets", "centerhead_cluster_groups", "comloss_group_confidence", "comloss_reweight", "box_trig_host", "box_trig4_host",
+    "points_in_any_box", "points_in_boxes_index", "boxes_bev", "nms", "centerhead_decode_nms", "dense_nhwc_bf16", "dense_gather_nhwc", "comaug_valid_mask", "centerhead_assign_targets", "centerhead_cluster_groups", "comloss_group_confidence", "comloss_reweight", "box_trig_host", "box_trig4_host",
 ]
 
 
@@ -590,6 +590,55 @@ class DenseFunction(torch.autograd.Function):
         return dense_gather(grad.contiguous().float(), coords, dtype=ctx.dtype), None, None, None
 
 
+def dense_nhwc_bf16(feats, coords, batch, shape, n_dev=None):
+    """f4: the BEV image of HeightCompression for a bf16 NHWC 2D backbone: logical shape (batch, C*D, H, W), bf16,
+    channels_last strides (memory [batch][H][W][C*D], channel c*D + z) — comb_dense_scatter_nhwc_bf16."""
+    lib = _lib.load()
+    _need(feats, feats.dtype, "feats")
+    _need(coords, torch.int32, "coords")
+    D, H, W = [int(x) for x in shape]
+    n, C = int(feats.shape[0]), int(feats.shape[1])
+    mem = torch.zeros((int(batch), H, W, C * D), dtype=torch.bfloat16, device=feats.device)
+    with _Scope("dense", n=n, n_dev=n_dev, C=C, cells=int(batch) * D * H * W, in_bytes=feats.element_size(), nhwc=True):
+        check(lib.comb_dense_scatter_nhwc_bf16(_p(feats), _dt(feats), _p(coords), n, _p(n_dev), int(batch), C, D, H, W,
+                                               _p(mem), _stream()), "comb_dense_scatter_nhwc_bf16")
+    return mem.permute(0, 3, 1, 2)
+
+
+def dense_gather_nhwc(grad, coords, C, D, dtype=torch.float32, n_dev=None):
+    """Adjoint of dense_nhwc_bf16: grad logical (batch, C*D, H, W) in channels_last memory (fp32 or bf16) -> (n, C)."""
+    lib = _lib.load()
+    _need(coords, torch.int32, "coords")
+    B, CD, H, W = [int(v) for v in grad.shape]
+    assert CD == C * D
+    mem = grad.permute(0, 2, 3, 1)
+    if not mem.is_contiguous():
+        mem = mem.contiguous()
+    if mem.dtype not in (torch.float32, torch.bfloat16):
+        mem = mem.float()
+    n = int(coords.shape[0])
+    out = torch.empty((n, C), dtype=dtype, device=grad.device)
+    with _Scope("dense", n=n, C=C, cells=B * D * H * W, in_bytes=mem.element_size(), gather=True, nhwc=True):
+        check(lib.comb_dense_gather_nhwc(_p(mem), _dt(mem), _p(coords), n, _p(n_dev), B, C, D, H, W, _p(out), _dt(out),
+                                         _stream()), "comb_dense_gather_nhwc")
+    return out
+
+
+class DenseNHWCFunction(torch.autograd.Function):
+    """dense_nhwc_bf16 with autograd (backward = comb_dense_gather_nhwc)."""
+
+    @staticmethod
+    def forward(ctx, feats, coords, batch, shape):
+        ctx.save_for_backward(coords)
+        ctx.dtype, ctx.C, ctx.D = feats.dtype, int(feats.shape[1]), int(shape[0])
+        return dense_nhwc_bf16(feats.contiguous(), coords, batch, shape)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (coords,) = ctx.saved_tensors
+        return dense_gather_nhwc(grad, coords, ctx.C, ctx.D, dtype=ctx.dtype), None, None, None
+
+
 # --------------------------------------------------------------------------------------------- box ops
 def box_trig_host(boxes_np):
     """(nb,2) float32 = (cosf(-rz), sinf(-rz)) from the host libm (bit-identical to the reference's)."""
@@ -823,3 +872,29 @@ def comloss_reweight(pred, radius_map, box_mask, mask, threshold, elongation, he
                                         1 if only_center else 0, 1 if active else 0, _p(box_mask), _p(mask), _stream()),
               "comb_comloss_reweight")
     return box_mask, mask
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# f3 — COMAug placement test (boxes.cu)
+def comaug_valid_mask(sampled_boxes, existed_boxes):
+    """database_sampler_v2.py:600-604 in one device round trip: numpy (S,7+) sampled and (E,7+) existing boxes in,
+    numpy bool (S,) out — True where a sampled box overlaps neither an existing box nor another sampled one.  The two
+    IoU matrices (CPU-flavour arithmetic, bit-exact with boxes_bev_iou_cpu) never leave the device."""
+    import numpy as np
+    lib = _lib.load()
+    dev = host_op_device()
+    sb = np.ascontiguousarray(np.asarray(sampled_boxes)[:, 0:7], dtype=np.float32)
+    eb = np.ascontiguousarray(np.asarray(existed_boxes)[:, 0:7], dtype=np.float32)
+    S, E = int(sb.shape[0]), int(eb.shape[0])
+    if S == 0:
+        return np.zeros((0,), dtype=bool)
+    with torch.cuda.device(dev):
+        a, ta = torch.from_numpy(sb).to(dev), torch.from_numpy(box_trig4_host(sb)).to(dev)
+        iou2 = boxes_bev(a, a, flavour="cpu", what="iou", trig_a=ta, trig_b=ta)
+        iou1 = None
+        if E > 0:
+            b, tb = torch.from_numpy(eb).to(dev), torch.from_numpy(box_trig4_host(eb)).to(dev)
+            iou1 = boxes_bev(a, b, flavour="cpu", what="iou", trig_a=ta, trig_b=tb)
+        valid = torch.empty((S,), dtype=torch.uint8, device=dev)
+        check(lib.comb_comaug_valid_mask(_p(iou1), _p(iou2), S, E, _p(valid), _stream()), "comb_comaug_valid_mask")
+        return valid.cpu().numpy().astype(bool)

@@ -10,6 +10,7 @@ All arithmetic runs in libcomb200 kernels; numpy in -> numpy out like the refere
 import numpy as np
 import torch
 
+from .. import ops as _ops
 from . import iou3d_nms_cuda as _iou
 from . import roiaware_pool3d_cuda as _roi
 
@@ -125,3 +126,26 @@ def remove_points_in_boxes3d(points, boxes3d):
     pts, np_in = _to_torch(points)
     inside_any = _roi.points_in_any_box_cpu(bxs, pts[:, 0:3])
     return _ret(pts[~inside_any], np_in)
+
+
+# ---- f3: the device side of a COMAug sampler step ----------------------------------------------------------------------
+def comaug_place_sampled_boxes(sampled_boxes, existed_boxes):
+    """The placement test of DataBaseSampler.__call__ (pcdet/datasets/augmentor/database_sampler_v2.py:600-611): which
+    of the `sampled_boxes` (S,7+) drawn from the ground-truth database may be pasted into a scene that already holds
+    `existed_boxes` (E,7+).  -> (valid_idx int64 (V,), existed_boxes with the valid sampled boxes appended), exactly
+    what the reference derives from its two boxes_bev_iou_cpu matrices; here one byte per sampled box crosses PCIe."""
+    sampled_boxes = np.asarray(sampled_boxes)
+    existed_boxes = np.asarray(existed_boxes)
+    valid_idx = _ops.comaug_valid_mask(sampled_boxes, existed_boxes).nonzero()[0]
+    valid = sampled_boxes[valid_idx]
+    return valid_idx, np.concatenate((existed_boxes, valid[:, :existed_boxes.shape[-1]]), axis=0)
+
+
+def comaug_add_to_scene(points, sampled_gt_boxes, obj_points, extra_width=(0.0, 0.0, 0.0)):
+    """The point-cloud side of DataBaseSampler.add_sampled_boxes_to_scene (database_sampler_v2.py:535-539): scene points
+    inside the sampled boxes enlarged by REMOVE_EXTRA_WIDTH are dropped (any-box kernel, P bytes back), the database
+    objects' points are put in front.  numpy in, numpy out."""
+    large = np.array(sampled_gt_boxes[:, 0:7], dtype=np.float32, copy=True)
+    large[:, 3:6] += np.asarray(extra_width, dtype=np.float32)[None, :]
+    kept = remove_points_in_boxes3d(points, large)
+    return np.concatenate([obj_points[:, :kept.shape[-1]], kept], axis=0)

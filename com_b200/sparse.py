@@ -26,6 +26,10 @@ class _Config:
     compute = os.environ.get("COMB200_COMPUTE", "bf16")
     # wgrad of the "bf16" training form: "bf16" = tcgen05 kernel (conv_wgrad.cu), "f32" = fp32 check kernel
     wgrad = os.environ.get("COMB200_WGRAD", "bf16")
+    # f4 — the 2D backbone (BaseBEVBackbone) on bf16 NHWC: "bf16" makes the reference's HeightCompression hand it the BEV
+    # image as channels-last bf16 (comb_dense_scatter_nhwc_bf16) and runs its forward under bf16 autocast; "f32"
+    # (default) is the reference's fp32 NCHW tensor.  COMB200_BEV=bf16.
+    bev = os.environ.get("COMB200_BEV", "f32")
 
 
 config = _Config()
@@ -115,6 +119,12 @@ class SparseConvTensor:
         if not channels_first:
             out = out.permute(0, 2, 3, 4, 1).contiguous()
         return out
+
+    def dense_bev_bf16(self):
+        """f4: HeightCompression's (N, C*D, H, W) image as channels-last bf16 (height_compression.py:21-24 in one kernel)."""
+        if torch.is_grad_enabled() and self.features.requires_grad:
+            return ops.DenseNHWCFunction.apply(self.features, self.indices, self.batch_size, self.spatial_shape)
+        return ops.dense_nhwc_bf16(self.features.contiguous(), self.indices, self.batch_size, self.spatial_shape)
 
     @property
     def sparity(self):

@@ -338,6 +338,23 @@ int comb_centerhead_decode_nms(const float* hm, const float* center, const float
                                float* out_scores, int* out_labels, int* out_counts, void* workspace,
                                size_t workspace_bytes, void* stream);
 
+/* ---- f4: the BEV tensor in channels-last bf16 -------------------------------------------------------------------------
+ * HeightCompression (pcdet/models/backbones_2d/map_to_bev/height_compression.py:21-24: dense() + view(N, C*D, H, W))
+ * for a 2D backbone (pcdet/models/backbones_2d/base_bev_backbone.py:81-112) that runs in bf16 NHWC: the rows are
+ * scattered into out[b][y][x][c*D + z] (bf16, [batch,H,W,C*D], ZERO-filled by the caller); feats are fp32 or bf16
+ * [n,C], coords int32 (b,z,y,x).  comb_dense_gather_nhwc is the adjoint (grad fp32 or bf16 in the same layout). */
+int comb_dense_scatter_nhwc_bf16(const void* feats, int dtype, const int* coords, int n_max, const int* n_dev, int batch,
+                                 int C, int D, int H, int W, void* out, void* stream);
+int comb_dense_gather_nhwc(const void* grad, int grad_dtype, const int* coords, int n_max, const int* n_dev, int batch,
+                           int C, int D, int H, int W, void* out, int dtype, void* stream);
+
+/* ---- f3: COMAug placement test ------------------------------------------------------------------------------------------
+ * The collision test of the COMAug database sampler (pcdet/datasets/augmentor/database_sampler_v2.py:600-604):
+ *   valid[i] = (max_j iou1[i][j] + max_j iou2[i][j]) == 0, iou2's diagonal taken as 0, iou1 replaced by iou2 when E == 0,
+ * from the two BEV IoU matrices (comb_boxes_bev, flavour 0: sampled x existing [S,E], sampled x sampled [S,S]) where they
+ * lie on the device; valid is S bytes. */
+int comb_comaug_valid_mask(const float* iou1, const float* iou2, int S, int E, unsigned char* valid, void* stream);
+
 /* ---- f1: CenterHead target assignment and the COM loss re-weighting -------------------------------------------------
  * Replaces the per-object Python loops of CurriculumCenterHead (pcdet/models/dense_heads/curriculum_center_head.py):
  * cluster (:431-473), assign_targets / assign_target_of_single_head (:120-296; CenterHead.assign_targets,

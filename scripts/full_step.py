@@ -131,9 +131,13 @@ def main():
                        "batch 2 Waymo-shaped frames, fwd + bwd + AdamW", "modules": [type(m).__name__ for m in model.module_list]}
     # fused_train_step: everything on; reference_head_loops: the reference's own Python target assignment / COM loss loops
     # (COMB_FUSED_TARGETS=0) on the fused backbone; module_path: additionally the per-module backbone
-    for label, env, tgt in (("fused_train_step", "1", "1"), ("reference_head_loops", "1", "0"), ("module_path", "0", "0")):
+    # fused_train_step_bev_bf16: additionally the 2D backbone on a channels-last bf16 image (f4, sparse.config.bev)
+    from com_b200 import sparse as _sparse
+    for label, env, tgt, bev in (("fused_train_step", "1", "1", "f32"), ("fused_train_step_bev_bf16", "1", "1", "bf16"),
+                                 ("reference_head_loops", "1", "0", "f32"), ("module_path", "0", "0", "f32")):
         os.environ["COMB_FUSED_TRAIN"] = env
         os.environ["COMB_FUSED_TARGETS"] = tgt
+        _sparse.config.bev = bev
         for _ in range(3):
             loss = step()
         torch.cuda.synchronize()
@@ -149,6 +153,7 @@ def main():
         out[label]["breakdown_ms"] = {k: round(v / 5, 3) for k, v in stages.items()}
     os.environ.pop("COMB_FUSED_TRAIN", None)
     os.environ.pop("COMB_FUSED_TARGETS", None)
+    _sparse.config.bev = "f32"
     # eval: forward + fused post-processing
     model.eval()
     with torch.no_grad():
@@ -160,6 +165,17 @@ def main():
             preds, _ = model(dict(batch))
         torch.cuda.synchronize()
     out["eval_forward_ms"] = 1e3 * (time.perf_counter() - t0) / 10
+    _sparse.config.bev = "bf16"
+    with torch.no_grad():
+        for _ in range(3):
+            preds, _ = model(dict(batch))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            preds, _ = model(dict(batch))
+        torch.cuda.synchronize()
+    out["eval_forward_bev_bf16_ms"] = 1e3 * (time.perf_counter() - t0) / 10
+    _sparse.config.bev = "f32"
     out["eval_detections"] = [int(p["pred_boxes"].shape[0]) for p in preds]
     print(json.dumps(out))
 

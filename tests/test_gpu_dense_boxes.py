@@ -214,3 +214,34 @@ def test_dense_scatter_matches_dense(C, dtype):
     n_dev = torch.tensor([1234], dtype=torch.int32, device="cuda")
     out2 = ops.dense_scatter(feats, cuda(coords), 3, shape, torch.zeros_like(want), n_dev=n_dev)
     assert torch.equal(out2, ops.dense(feats[:1234].contiguous(), cuda(coords[:1234]), 3, shape))
+
+
+# ---- f4: the BEV image in channels-last bf16 ---------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dense_nhwc_bf16_equals_dense_view_cast(dtype):
+    """comb_dense_scatter_nhwc_bf16 == dense().view(N, C*D, H, W).to(bf16) in channels_last memory, bit for bit, and its
+    adjoint gathers exactly the cells of the rows (HeightCompression, height_compression.py:21-24)."""
+    from com_b200 import ops
+    rng = np.random.default_rng(3)
+    B, D, H, W, C, n = 3, 2, 47, 52, 128, 2500
+    cells = rng.choice(B * D * H * W, size=n, replace=False)
+    coords = np.stack(np.unravel_index(cells, (B, D, H, W)), axis=1).astype(np.int32)
+    feats = torch.from_numpy(rng.normal(size=(n, C)).astype(np.float32)).cuda().to(dtype)
+    cd = torch.from_numpy(coords).cuda()
+    want = ops.dense(feats, cd, B, [D, H, W]).view(B, C * D, H, W).to(torch.bfloat16)
+    got = ops.dense_nhwc_bf16(feats, cd, B, [D, H, W])
+    assert got.shape == want.shape and got.dtype == torch.bfloat16
+    assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, want)
+    # adjoint, fp32 and bf16 gradients, any memory format
+    g = torch.from_numpy(rng.normal(size=(B, C * D, H, W)).astype(np.float32)).cuda()
+    want_rows = ops.dense_gather(g.view(B, C, D, H, W).contiguous(), cd, dtype=torch.float32)
+    for grad in (g, g.contiguous(memory_format=torch.channels_last)):
+        assert torch.equal(ops.dense_gather_nhwc(grad, cd, C, D, dtype=torch.float32), want_rows)
+    gb = g.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    assert torch.equal(ops.dense_gather_nhwc(gb, cd, C, D, dtype=torch.float32), ops.dense_gather(
+        gb.float().view(B, C, D, H, W).contiguous(), cd, dtype=torch.float32))
+    # autograd
+    f2 = feats.clone().requires_grad_(True)
+    out = ops.DenseNHWCFunction.apply(f2, cd, B, [D, H, W])
+    (out.float() * g).sum().backward()
+    assert torch.allclose(f2.grad.float(), want_rows.to(dtype).float(), rtol=1e-2, atol=1e-2)
