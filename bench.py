@@ -497,16 +497,20 @@ def train_leg(torch, frames, world=1, local_rank=0):
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank])
     opt = torch.optim.SGD(net.parameters(), lr=1e-3)
     vfe = models.MeanVFE(None, 5)
+    flat_sync = cdist.FlatGradSync(net.parameters())
+    state = {"model": model, "sync": None}
 
     def step():
         r = ops.voxelize(pts, offs, synth.VOXEL_SIZE, synth.POINT_CLOUD_RANGE, synth.MAX_POINTS_PER_VOXEL,
                          synth.MAX_NUMBER_OF_VOXELS)
         m = int(r["counts"][2])
         bd = vfe({"voxels": r["voxels"][:m], "voxel_num_points": r["num_points"][:m]})
-        bd = model({"batch_size": 2, "voxel_features": bd["voxel_features"], "voxel_coords": r["coords"][:m].float()})
+        bd = state["model"]({"batch_size": 2, "voxel_features": bd["voxel_features"], "voxel_coords": r["coords"][:m].float()})
         loss = bd["encoded_spconv_tensor"].features.float().square().mean()
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        if state["sync"] is not None:
+            state["sync"]()
         opt.step()
         return loss.detach()
 
@@ -527,6 +531,10 @@ def train_leg(torch, frames, world=1, local_rank=0):
             # ReLU / residual and their backward in libcomb200 kernels, W and W^T packed once per optimizer step; the
             # other three labels are the module path (every conv / BatchNorm1d / ReLU called one by one under autograd)
             net.fused = label == "fused_train_step"
+            # the fused step hands over all gradients at once: one flat all-reduce (com_b200.dist.FlatGradSync) instead
+            # of torch DDP's bucket reducer; the module-path labels keep DDP, as the reference's tools/train.py does
+            use_flat = world > 1 and net.fused
+            state["model"], state["sync"] = (net, flat_sync) if use_flat else (model, None)
             step()
             step()
             cdist.barrier()
@@ -866,8 +874,11 @@ def ours(args):
         conv = fam.get("spconv_fwd_bf16", dict(ms=1e-9, flops=0, bytes=0, launches=1))
         conv_s = conv["ms"] / 1e3
         tf = conv["flops"] / conv_s / 1e12
-        conv_impl = "spconv_tc_kernel (A in shared memory)" if os.environ.get("COMB_CONV_IMPL", "ts")[:2] == "ss" \
-            else "spconv_ts_kernel (A gathered into tensor memory)"
+        conv_impl = {"ss": "spconv_tc_kernel (A in shared memory)", "ts": "spconv_ts_kernel (A gathered into tensor memory)",
+                     "tr": "spconv_tr_kernel (one gather thread per output row) where the weights fit, else spconv_ts_kernel"
+                     }.get(os.environ.get("COMB_CONV_IMPL", "")[:2],
+                           "spconv_tr_kernel (Cin <= 32: one gather thread per output row, A in tensor memory) + "
+                           "spconv_ts_kernel (Cin >= 64: 16x256b fragments into tensor memory)")
         roof = {"bound": "tensor", "kernel": "%s: tcgen05 gather-GEMM, 21 launches/step" % conv_impl,
                 "achieved": tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": tf / peaks["tf_sust"],
                 "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks["src"],

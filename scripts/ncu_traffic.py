@@ -50,7 +50,7 @@ def main():
     for rep in reps:
         allk += parse(rep)
     json.dump(allk, open(os.path.join(root, "profiles", "%s_ncu_summary.json" % tag), "w"), indent=1)
-    conv = [k for k in allk if "spconv_ts_kernel" in k["kernel"]]
+    conv = [k for k in allk if "spconv_ts_kernel" in k["kernel"] or "spconv_tr_kernel" in k["kernel"]]
     if conv:
         t = sum(k.get("dram_read_bytes", 0) + k.get("dram_write_bytes", 0) for k in conv) / len(conv)
         json.dump({"dram_bytes_per_launch": t, "launches_captured": len(conv),

@@ -31,3 +31,24 @@ oc, cnt = ops.conv_out_coords(coords, 2, oshape, *cv, m * 8)
 x = ops.permute_rows(r["mean"], perm, scatter=True)
 torch.cuda.synchronize()
 print("racecheck target ok: %d voxels, %d level-2 rows, %d pairs" % (m, int(oidx.count.item()), int((nbr >= 0).sum())))
+
+# r2 additions: the row-per-thread tcgen05 conv (mbarrier / tensor-memory hand-shakes), target assignment (atomicMax
+# heat maps, block scan), COM loss re-weighting (object-ordered window writes), COMAug placement reduce
+feat16 = ops.cast_pad(torch.randn((int(idx.count.item()), 16), device="cuda"), 16)
+w16 = ops.pack_weight_bf16(torch.randn((16, 27, 16), device="cuda") / 20)
+y = ops.spconv_fwd_bf16(feat16, w16, 27, 16, nbr[:, : feat16.shape[0]].contiguous())
+gt = torch.zeros((2, 40, 8), device="cuda")
+gt[:, :30, 0:2] = (torch.rand((2, 30, 2), device="cuda") - 0.5) * 100
+gt[:, :30, 3:6] = torch.tensor([4.5, 2.0, 1.6], device="cuda")
+gt[:, :30, 7] = torch.randint(1, 4, (2, 30), device="cuda").float()
+grp = ops.centerhead_cluster_groups(gt, torch.ones((2, 40), device="cuda"), torch.rand((2, 40), device="cuda"),
+                                    torch.randint(0, 4, (2, 40), device="cuda"))
+cls_map = torch.tensor([-1, 0, 1, 2], dtype=torch.int32, device="cuda")
+hm, rb, inds, mask, rmap = ops.centerhead_assign_targets(gt, torch.full((2, 40), 9.0, device="cuda"), grp, cls_map, 3, (188, 188), 8,
+                                                         [-75.2, -75.2, -2, 75.2, 75.2, 4], [0.1, 0.1, 0.15])
+pred = torch.rand((2, 3, 188, 188), device="cuda").clamp(1e-4, 1 - 1e-4)
+ops.comloss_group_confidence(pred, rmap, 3, 96)
+ops.comloss_reweight(pred, rmap, mask.clone(), torch.ones_like(hm), 0.05, -10.0, 1.0)
+ops.comaug_valid_mask(synth.make_clustered_boxes(40, seed=1), synth.make_boxes(60, seed=2))
+torch.cuda.synchronize()
+print("r2 kernels ok: conv_tr rows %d, targets %d" % (int(y.shape[0]), int(mask.sum())))

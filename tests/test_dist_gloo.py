@@ -24,8 +24,25 @@ def _worker(rank, world, port, q):
     cdist.barrier()
     t = cdist.max_over_ranks(10.0 + r, device="cpu")
     n = cdist.sum_over_ranks(len(mine), device="cpu")
-    q.put((r, mine, t, n))
+    # FlatGradSync: one flat all-reduce == the mean of the ranks' gradients (what DistributedDataParallel produces);
+    # parameters without a gradient on this rank count as zeros; a single-element and a bf16 parameter ride along
+    import torch
     import torch.distributed as dist
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(s_)) for s_ in ((3, 4), (5,), (1,))] + [torch.nn.Parameter(torch.zeros((2, 2), dtype=torch.bfloat16))]
+    gen = torch.Generator().manual_seed(100 + r)
+    for i, p in enumerate(params):
+        if not (r == 1 and i == 1):
+            p.grad = torch.randn(p.shape, generator=gen).to(p.dtype)
+    mine_g = [None if p.grad is None else p.grad.clone().float() for p in params]
+    cdist.FlatGradSync(params)()
+    gathered = [None, None]
+    dist.all_gather_object(gathered, mine_g)
+    ok = True
+    for i, p in enumerate(params):
+        want = sum((g[i] if g[i] is not None else torch.zeros(p.shape)) for g in gathered) / w
+        ok = ok and p.grad is not None and p.grad.dtype == p.dtype and torch.allclose(p.grad.float(), want, atol=1e-2 if i == 3 else 1e-6)
+    q.put((r, mine, t, n, ok))
     dist.destroy_process_group()
 
 
@@ -50,6 +67,7 @@ def test_two_ranks_gloo():
     assert res[0][1] == [0, 2, 4, 6] and res[1][1] == [1, 3, 5]
     assert res[0][2] == res[1][2] == 11.0           # max over ranks
     assert res[0][3] == res[1][3] == 7.0            # every frame processed exactly once
+    assert res[0][4] and res[1][4]                  # flat gradient all-reduce == mean over ranks
 
 
 def test_single_process_is_a_noop():
