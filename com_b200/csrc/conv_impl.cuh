@@ -6,6 +6,7 @@
 // The packed weight image differs between the two (the ts form permutes K inside a chunk), so the choice is
 // made once per process and used by both comb_spconv_pack_weight_bf16 and comb_spconv_fwd_bf16.
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace comb {
@@ -31,6 +32,30 @@ struct ConvFwdArgs {
   int sc = 2;       // conv_ts: chunks of each row tile per A stage (set by launch_ts)
   int ablate = 0;   // conv_ts: COMB_TS_ABLATE bit mask — pipeline pieces switched off for timing experiments (results are garbage)
 };
+
+// Launch, optionally with programmatic stream serialization (COMB_PDL=1; the kernels call griddepcontrol.wait before
+// they read anything an earlier kernel wrote, so their set-up can overlap the tail of the previous kernel of the stream,
+// also inside a captured graph).  r2 A/B in the bench, same box, two runs each: 1.102 / 1.107 ms per step with it against
+// 1.099 / 1.093 without — the 2.2 us of set-up per launch are not what separates the 21 convs of the chain — so the
+// default is a plain launch.
+template <typename Kernel>
+static inline cudaError_t launch_pdl(Kernel kernel, int grid, int block, size_t smem, cudaStream_t stream, const ConvFwdArgs& p) {
+  static const bool on = [] {
+    const char* e = getenv("COMB_PDL");
+    return e && e[0] == '1';
+  }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = on ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
 
 int ts_fwd_bf16(const ConvFwdArgs& p, int Cin_p, int Cout, cudaStream_t stream);
 // natural: K in tap-major / channel-minor order (conv_tr.cu and the pipelined conv_ts variant); otherwise the permuted

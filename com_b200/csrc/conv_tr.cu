@@ -95,13 +95,11 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tr_kernel(ConvFwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int no = eff_n(p.no_max, p.no_dev);             // real row count (device side): capacities run 1.5-2x above it
-  const int ntiles = (no + kBM - 1) / kBM;
+  pdl_launch_dependents();                           // the next kernel of the stream may set itself up behind our tail
   const int K = p.K;
   const int NCHT = Cfg::num_chunks(K);               // chunks of a tile's K range
   constexpr int NCH = Cfg::kSlabChunksMax;           // chunks per slab
   const int SPT = (NCHT + NCH - 1) / NCH;            // slabs per tile
-  const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   const uint32_t bars = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = bars + 1024u;
@@ -133,6 +131,18 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tr_kernel(ConvFwdArgs p) {
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bars + kTmemSlot) : "memory");
     if (tmem_base != 0) __trap();
   }
+  if (warp == kMmaWarp && elect_one_sync()) {
+    // the weight image (packed once per weight version, long before this step): one bulk copy, resident for the CTA's life
+    const uint32_t bytes = (uint32_t)NCHT * Cfg::kBBytes;
+    mbar_arrive_expect_tx(bars + kBarB, bytes);
+    bulk_copy_g2s(w_base, p.wpacked, bytes, bars + kBarB);
+  }
+  // ---- everything above touched only this CTA's own state and constant data; from here on the earlier kernels of the
+  // stream (the producer of p.in / p.nbr / p.no_dev / p.residual) are complete
+  pdl_wait();
+  const int no = eff_n(p.no_max, p.no_dev);             // real row count (device side): capacities run 1.5-2x above it
+  const int ntiles = (no + kBM - 1) / kBM;
+  const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (p.ablate & 64) {
     // timing experiment: set-up and tear-down only
@@ -281,13 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tr_kernel(ConvFwdArgs p) {
     constexpr uint32_t kChunkStep = (uint32_t)Cfg::kBBytes >> 4;      // descriptor units between 64-wide K chunks
     const int AB = p.ablate;
     if (elect_one_sync()) {
-      {
-        // the weight image: one bulk copy, resident for the life of the CTA
-        const uint32_t bytes = (uint32_t)NCHT * Cfg::kBBytes;
-        mbar_arrive_expect_tx(bars + kBarB, bytes);
-        bulk_copy_g2s(w_base, p.wpacked, bytes, bars + kBarB);
-        mbar_wait(bars + kBarB, 0);
-      }
+      mbar_wait(bars + kBarB, 0);          // the weight image (requested before the grid dependency wait)
       uint32_t j = 0;
       const uint64_t desc0 = make_desc_sw128(w_base);
       const uint64_t desc_hi = desc0 & 0xFFFFFFFF00000000ull;
@@ -357,7 +361,7 @@ int launch_tr(const ConvFwdArgs& p_in, cudaStream_t stream) {
     COMB_CUDA(cudaFuncSetAttribute(spconv_tr_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   const int ntiles = cdiv(p.no_max, kBM);
   const int grid = ntiles < sm_count() ? ntiles : sm_count();
-  spconv_tr_kernel<CIN, COUT><<<grid, kThreads, smem, stream>>>(p);
+  COMB_CUDA(launch_pdl(spconv_tr_kernel<CIN, COUT>, grid, kThreads, smem, stream, p));
   COMB_LAUNCH_CHECK();
   return COMB_OK;
 }

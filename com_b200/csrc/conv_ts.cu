@@ -151,9 +151,8 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();                           // the next kernel of the stream may set itself up behind our tail
   if (TRACE && tid == 0) dbg_cta_time(p.dbg, 0);
-  const int no = eff_n(p.no_max, p.no_dev);
-  const int ntiles = (no + kBM - 1) / kBM;
   const int K = p.K;
   const int nchunks = Cfg::num_chunks(K);
   const int kpad = Cfg::k_pad(K);
@@ -172,6 +171,53 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   const uint32_t stage_cols = (uint32_t)(2 * SC * 32);
   const int NS = (512 - Cfg::d_cols(K)) / (int)stage_cols;     // A stages
   const uint32_t colA = (uint32_t)Cfg::d_cols(K);
+  const int nst = (nchunks + SC - 1) / SC;           // stages per super-tile (the last one may be partial)
+
+  // shared memory map (1024-byte aligned): [barriers 1 KB] [weights: resident image | NB streamed 2-chunk stages]
+  // [index tiles NI x kpad x 128]
+  const uint32_t bars = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = bars + 1024u;
+  const uint32_t idx_base = w_base + (bres ? nchunks * Cfg::kBBytes : NB * SC * Cfg::kBBytes);
+  const uint32_t idx_buf_bytes = (uint32_t)kpad * kBM * 4;
+
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(bars + kBarFull + 8 * s, kGatherWarps);
+      mbar_init(bars + kBarEmpty + 8 * s, 2);          // both MMA threads commit
+    }
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(bars + kBarBFull + 8 * s, 1);
+      mbar_init(bars + kBarBEmpty + 8 * s, 2);
+      mbar_init(bars + kBarTFull + 8 * s, 1);
+      mbar_init(bars + kBarTEmpty + 8 * s, 4);
+      mbar_init(bars + kBarIdx + 8 * s, 32);
+      mbar_init(bars + kBarIdxFree + 8 * s, kGatherWarps);
+    }
+    mbar_init(bars + kBarB, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + kTmemSlot), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // index-tile rows of the padding offsets (k in [K, kpad)) stay -1 for the whole kernel
+  for (int e = tid; e < NI * (kpad - K) * kBM; e += kThreads) {
+    const int buf = e / ((kpad - K) * kBM), r = e - buf * (kpad - K) * kBM;
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(idx_base + buf * idx_buf_bytes + (K * kBM + r) * 4), "r"(-1) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bars + kTmemSlot) : "memory");
+  if (TRACE && tid == 0) dbg_cta_time(p.dbg, 1);
+
+  // ---- everything above touched only this CTA's own state; from here on the earlier kernels of the stream (the
+  // producers of p.in / p.nbr / p.no_dev / p.residual) are complete (programmatic dependent launch, tc_util.cuh)
+  pdl_wait();
+  const int no = eff_n(p.no_max, p.no_dev);
+  const int ntiles = (no + kBM - 1) / kBM;
   // Passes.  A pass walks T row tiles; with T = 2 the last wave of passes is split into single-tile passes when
   // that shortens it (r <= grid/2 leftover super-tiles become 2r half passes on 2r CTAs: the absent second tile
   // is neither gathered nor multiplied).
@@ -216,48 +262,6 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   } else {
     my_super = nsuper > (int)blockIdx.x ? (nsuper - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   }
-  const int nst = (nchunks + SC - 1) / SC;           // stages per super-tile (the last one may be partial)
-
-  // shared memory map (1024-byte aligned): [barriers 1 KB] [weights: resident image | NB streamed 2-chunk stages]
-  // [index tiles NI x kpad x 128]
-  const uint32_t bars = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t w_base = bars + 1024u;
-  const uint32_t idx_base = w_base + (bres ? nchunks * Cfg::kBBytes : NB * SC * Cfg::kBBytes);
-  const uint32_t idx_buf_bytes = (uint32_t)kpad * kBM * 4;
-
-  if (tid == 0) {
-    for (int s = 0; s < 4; ++s) {
-      mbar_init(bars + kBarFull + 8 * s, kGatherWarps);
-      mbar_init(bars + kBarEmpty + 8 * s, 2);          // both MMA threads commit
-    }
-    for (int s = 0; s < 8; ++s) {
-      mbar_init(bars + kBarBFull + 8 * s, 1);
-      mbar_init(bars + kBarBEmpty + 8 * s, 2);
-      mbar_init(bars + kBarTFull + 8 * s, 1);
-      mbar_init(bars + kBarTEmpty + 8 * s, 4);
-      mbar_init(bars + kBarIdx + 8 * s, 32);
-      mbar_init(bars + kBarIdxFree + 8 * s, kGatherWarps);
-    }
-    mbar_init(bars + kBarB, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == kMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + kTmemSlot), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  // index-tile rows of the padding offsets (k in [K, kpad)) stay -1 for the whole kernel
-  for (int e = tid; e < NI * (kpad - K) * kBM; e += kThreads) {
-    const int buf = e / ((kpad - K) * kBM), r = e - buf * (kpad - K) * kBM;
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(idx_base + buf * idx_buf_bytes + (K * kBM + r) * 4), "r"(-1) : "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bars + kTmemSlot) : "memory");
-  if (TRACE && tid == 0) dbg_cta_time(p.dbg, 1);
-
   if (PIPE == 1) {
     // Register budget: the CTA owns 768 x 80 = 61440 registers for its whole life (setmaxnreg only moves registers
     // inside the CTA's pool: asking for more than the other warpgroups release never completes — r2 lesson, a 104-register
@@ -755,10 +759,10 @@ int launch_ts(const ConvFwdArgs& p_in, cudaStream_t stream) {
   }
   const int nsuper = cdiv(cdiv(p.no_max, kBM), Cfg::tiles_per_pass(p.K));
   const int grid = nsuper < sm_count() ? nsuper : sm_count();
-  if (p.dbg != nullptr) spconv_ts_kernel<CIN, COUT, true, 0><<<grid, kThreads, smem, stream>>>(p);   // pipeline trace build
-  else if (ts_pipe() == 1) spconv_ts_kernel<CIN, COUT, false, 1><<<grid, kThreads, smem, stream>>>(p);
-  else if (ts_pipe() == 2) spconv_ts_kernel<CIN, COUT, false, 2><<<grid, kThreads, smem, stream>>>(p);
-  else spconv_ts_kernel<CIN, COUT, false, 0><<<grid, kThreads, smem, stream>>>(p);
+  if (p.dbg != nullptr) COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, true, 0>, grid, kThreads, smem, stream, p));   // pipeline trace build
+  else if (ts_pipe() == 1) COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, false, 1>, grid, kThreads, smem, stream, p));
+  else if (ts_pipe() == 2) COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, false, 2>, grid, kThreads, smem, stream, p));
+  else COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, false, 0>, grid, kThreads, smem, stream, p));
   COMB_LAUNCH_CHECK();
   return COMB_OK;
 }

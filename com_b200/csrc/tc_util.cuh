@@ -81,6 +81,13 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still draining; everything BEFORE pdl_wait() must touch nothing an
+// earlier kernel writes (barrier set-up, tensor-memory allocation, the constant weight image), everything after it
+// sees all earlier kernels complete.  pdl_launch_dependents() lets the successor's CTAs be scheduled as soon as SMs free up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
