@@ -497,7 +497,8 @@ def train_leg(torch, frames, world=1, local_rank=0):
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank])
     opt = torch.optim.SGD(net.parameters(), lr=1e-3)
     vfe = models.MeanVFE(None, 5)
-    flat_sync = cdist.FlatGradSync(net.parameters())
+    from com_b200 import train as ctrain
+    flat_sync = cdist.FlatGradSync(net.parameters(), flat_provider=lambda: getattr(ctrain.get_trainer(net), "last_flat", None))
     state = {"model": model, "sync": None}
 
     def step():
@@ -548,6 +549,8 @@ def train_leg(torch, frames, world=1, local_rank=0):
             ms = cdist.max_over_ranks(e0.elapsed_time(e1) / reps)
             res[label] = {"ms_per_step": ms, "frames_per_s": 2e3 * world / ms,
                           "loss_finite": bool(np.isfinite(float(last)))}
+            if use_flat:
+                res[label]["grad_sync"] = "FlatGradSync: one all-reduce%s" % (", in place on the backward graph's buffer" if flat_sync.in_place else "")
         # the tcgen05 wgrad launches of one step, replayed back to back behind a spin kernel (launches queued, no host
         # gaps) with CUDA events around each: per-layer device time and algorithmic TFLOP/s (2 * pairs * Cin * Cout)
         class _Capture:

@@ -70,14 +70,34 @@ class FlatGradSync:
         sync = FlatGradSync(net.parameters()); ... loss.backward(); sync(); opt.step()
     """
 
-    def __init__(self, params, group=None):
+    def __init__(self, params, group=None, flat_provider=None):
+        """flat_provider: optional callable returning the ONE tensor that already holds every gradient (the fused train
+        step's backward graph writes them into one buffer and autograd hands out views of it): the all-reduce then runs
+        in place on that buffer and nothing is gathered or copied back."""
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.sizes = [p.numel() for p in self.params]
+        self.flat_provider = flat_provider
         self.flat = None
+        self.in_place = False
+
+    def _views_of(self, flat):
+        """True when every p.grad is a dense view into `flat` (so reducing `flat` reduces the gradients)."""
+        if flat is None or flat.dtype != torch.float32 or flat.numel() != sum(self.sizes):
+            return False
+        lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+        return all(p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous()
+                   and lo <= p.grad.data_ptr() and p.grad.data_ptr() + p.grad.numel() * 4 <= hi for p in self.params)
 
     def __call__(self):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        flat = self.flat_provider() if self.flat_provider is not None else None
+        self.in_place = self._views_of(flat)
+        if self.in_place:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(dist.get_world_size(self.group))
+            self.flat = flat
             return
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
         flat = torch.cat([g.reshape(-1).float() for g in grads])

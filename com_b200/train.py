@@ -51,6 +51,7 @@ class FusedTrainer:
         self._capturing = False
         self.relu = True            # tests switch the ReLUs off to get a smooth loss (gradient parity without sign flips)
         self.last = None            # state of the last forward (levels for multi_scale_3d_features, counts)
+        self.last_flat = None       # flat buffer holding every parameter gradient of the last graphed backward
 
     @staticmethod
     def _plan(m):
@@ -310,11 +311,13 @@ class _TrainFn(torch.autograd.Function):
                 g.g_bwd.replay()
                 flat = g.flat.clone()                            # the graph's output buffer is rewritten by the next replay
                 grads = [t.view(sh) for t, sh in zip(torch.split(flat, g.sizes), g.shapes)]
+                tr.last_flat = flat                              # all parameter gradients of this step, one buffer (dist.FlatGradSync)
             else:
                 cap5 = int(st["lv"][5]["x"].shape[0])
                 d = torch.zeros((cap5, dout.shape[1]), dtype=torch.bfloat16, device=dout.device)
                 d[: dout.shape[0]] = dout.to(torch.bfloat16)
                 grads = tr.backward(st, d)
+                tr.last_flat = None
         ctx.st = None
         return (None, None, None, None) + tuple(grads)
 

@@ -42,6 +42,17 @@ def _worker(rank, world, port, q):
     for i, p in enumerate(params):
         want = sum((g[i] if g[i] is not None else torch.zeros(p.shape)) for g in gathered) / w
         ok = ok and p.grad is not None and p.grad.dtype == p.dtype and torch.allclose(p.grad.float(), want, atol=1e-2 if i == 3 else 1e-6)
+    # in-place form: the gradients are views of one flat buffer (what the fused train step's backward graph hands out)
+    flat = torch.randn(20, generator=gen)
+    mine_f = flat.clone()
+    ps = [torch.nn.Parameter(torch.zeros(s_)) for s_ in ((3, 4), (8,))]
+    ps[0].grad, ps[1].grad = flat[:12].view(3, 4), flat[12:]
+    sync = cdist.FlatGradSync(ps, flat_provider=lambda: flat)
+    sync()
+    both = [None, None]
+    dist.all_gather_object(both, mine_f)
+    ok = ok and sync.in_place and torch.allclose(ps[0].grad.reshape(-1), ((both[0] + both[1]) / w)[:12]) \
+        and torch.allclose(ps[1].grad, ((both[0] + both[1]) / w)[12:])
     q.put((r, mine, t, n, ok))
     dist.destroy_process_group()
 
