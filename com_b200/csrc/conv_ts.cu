@@ -706,7 +706,10 @@ static int ts_pipe() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("COMB_TS_PIPE");
-    v = e ? atoi(e) : 0;      // 0 (default): r1 loop; 1: pipelined gather; 2: r1 loop with the pipelined variant's register budget
+    v = e ? atoi(e) : 0;      // 0 (default): r1 loop; 1: pipelined gather; 2: sleep-free background waits
+#ifndef COMB_TS_EXPERIMENTS
+    v = 0;                    // the variants are not part of the product library (nvcc -DCOMB_TS_EXPERIMENTS builds them)
+#endif
   }
   return v;
 }
@@ -749,9 +752,11 @@ int launch_ts(const ConvFwdArgs& p_in, cudaStream_t stream) {
   static thread_local DevOnce configured;   // per device: the attribute is a per-device property
   if (configured.first()) {
     COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+#ifdef COMB_TS_EXPERIMENTS
     COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
     COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+#endif
   }
   if (smem > 227 * 1024 - 1024 || (!bres && nb < 2)) {
     set_error("comb_spconv_fwd_bf16: shared memory %zu exceeds the per-CTA limit", smem);
@@ -760,8 +765,10 @@ int launch_ts(const ConvFwdArgs& p_in, cudaStream_t stream) {
   const int nsuper = cdiv(cdiv(p.no_max, kBM), Cfg::tiles_per_pass(p.K));
   const int grid = nsuper < sm_count() ? nsuper : sm_count();
   if (p.dbg != nullptr) COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, true, 0>, grid, kThreads, smem, stream, p));   // pipeline trace build
+#ifdef COMB_TS_EXPERIMENTS     // the two measured-and-rejected gather variants (software-pipelined gather, sleep-free waits): built on demand only
   else if (ts_pipe() == 1) COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, false, 1>, grid, kThreads, smem, stream, p));
   else if (ts_pipe() == 2) COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, false, 2>, grid, kThreads, smem, stream, p));
+#endif
   else COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, false, 0>, grid, kThreads, smem, stream, p));
   COMB_LAUNCH_CHECK();
   return COMB_OK;

@@ -96,6 +96,35 @@ def test_assign_targets_point_filter_is_epoch_gated():
             assert torch.equal(got[key][0], want[key][0]), (epoch, key)
 
 
+def test_empty_and_all_padding_ground_truth():
+    """Frames without objects (M = 0) and frames whose gt rows are all padding (class 0): zero targets, as the
+    reference produces; the loss runs on them (no positives: `loss = -neg_loss`)."""
+    E = ref_py.EasyDict
+    ch = ref_py.load("pcdet.models.dense_heads.curriculum_center_head")
+    lu = ref_py.load("pcdet.utils.loss_utils")
+    head = fake_head(ch, E)
+    for M in (0, 6):
+        gt = torch.zeros((2, M, 8), device="cuda")
+        npgt = torch.zeros((2, M), device="cuda")
+        grp = torch.zeros((2, M), dtype=torch.int64, device="cuda")
+        want = ch.CurriculumCenterHead.assign_targets.reference(head, gt.clone(), feature_map_size=(188, 188), npgt=npgt, true_object=grp)
+        got = center_targets.assign_targets(head, gt, feature_map_size=(188, 188), npgt=npgt, true_object=grp)
+        for key in ("heatmaps", "inds", "masks", "radius_map", "heatmap_mask", "target_boxes"):
+            assert got[key][0].shape == want[key][0].shape and torch.equal(got[key][0], want[key][0]), (M, key)
+        assert ops.centerhead_cluster_groups(gt, npgt, npgt, npgt).shape == (2, M)
+    pred = torch.rand((2, 3, 188, 188), device="cuda").clamp(1e-4, 1 - 1e-4)
+    outs = []
+    for fn in (lu.FocalLossCenterCurriculum.neg_loss.reference, lu.FocalLossCenterCurriculum.neg_loss):
+        mod = loss_module(lu, E)
+        outs.append(fn(mod, pred, got["heatmaps"][0], got["radius_map"][0], got["masks"][0].clone(),
+                       mask=got["heatmap_mask"][0].clone(), epoch=1))
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-6) and torch.equal(outs[0][1], outs[1][1])
+    # the device side of a COMAug step with nothing to place
+    from com_b200.pcdet_ops import box_ops
+    idx, ex = box_ops.comaug_place_sampled_boxes(np.zeros((0, 7), np.float32), np.zeros((3, 7), np.float32))
+    assert idx.shape == (0,) and ex.shape == (3, 7)
+
+
 def loss_module(lu, E, **curriculum):
     cfg = E(LOSS_CURRICULUM=E(**curriculum))
     mod = lu.FocalLossCenterCurriculum(cfg, conf_shape=(3, 96))

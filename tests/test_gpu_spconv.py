@@ -211,11 +211,12 @@ def test_module_autograd_matches_oracle():
     assert rel_err(z.features.detach().cpu().numpy(), want) < TOL_F32
 
 
-@pytest.mark.parametrize("env", [{"COMB_CONV_IMPL": "ss"}, {"COMB_TS_PIPE": "1"}, {"COMB_TS_BLOCKED": "1", "COMB_TS_NI": "8", "COMB_TS_NB": "8"}])
+@pytest.mark.parametrize("env", [{"COMB_CONV_IMPL": "ss"}, {"COMB_CONV_IMPL": "ts"}, {"COMB_CONV_IMPL": "tr"}, {"COMB_PDL": "1"},
+                                 {"COMB_CONV_IMPL": "ts", "COMB_TS_BLOCKED": "1", "COMB_TS_NI": "8", "COMB_TS_NB": "8"}])
 def test_alternate_conv_kernels_stay_correct(env):
-    """The documented A/B switches (shared-memory-A tcgen05 kernel; software-pipelined gather with 8-byte
-    direct-to-fragment loads and natural K order; blocked tile assignment with deep rings) are read once per process,
-    so each is exercised in a child process: bf16 forward vs the oracle, 1e-4."""
+    """The documented A/B switches (shared-memory-A tcgen05 kernel; conv_ts or conv_tr forced for every layer shape;
+    programmatic dependent launch; blocked tile assignment with deep rings) are read once per process, so each is
+    exercised in a child process: bf16 forward vs the oracle, 1e-4."""
     import os
     import subprocess
     import sys
