@@ -153,7 +153,11 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tr_kernel(ConvFwdArgs p) {
     // loads and the NP tcgen05.st of a slab are issued back to back with nothing but address arithmetic between them.
     // (r2 A/B: a rotating window — store piece i of slab n, immediately request piece i of slab n+1 into the freed
     // registers, indices two slabs ahead — keeps the same NP rows in flight and measured SLOWER, 27.1 vs 22.5 us on
-    // the 16x16 level-1 layer: the window cannot hold more than one slab, and ptxas moves the loads behind the stores.)
+    // the 16x16 level-1 layer: the window cannot hold more than one slab, and ptxas moves the loads behind the stores.
+    // Also measured: TWO register sets of 3 pieces with slabs of 3 chunks in a ring of 4 slots — the rows of slab n+1
+    // requested before slab n is stored, so a batch of loads is always in flight — 27.9 vs 22.5 us at 16x16, 48.9 vs
+    // 45.6 at 32x32: each slab costs ~900 cycles of wait / tcgen05.wait::st / fence / arrive latencies whatever its
+    // size, and three slabs per tile cost more than the hidden round trip saves.)
     constexpr int NP = Cfg::kSlabChunksMax;           // pieces per thread per slab = chunks per slab
     const int q = warp & 3, r = warp >> 2;            // row quarter, quarter of the slab's K range
     const char* in = reinterpret_cast<const char*>(p.in);
