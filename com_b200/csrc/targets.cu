@@ -308,9 +308,8 @@ extern "C" int comb_centerhead_assign_targets(const float* gt_boxes, const float
   COMB_CHECK_ARG(max_objs >= 1 && max_objs <= kMaxObjsCap, "comb_centerhead_assign_targets: NUM_MAX_OBJS %d outside [1,%d]",
                  max_objs, kMaxObjsCap);
   COMB_CHECK_ARG(R == 4 || R == 5, "comb_centerhead_assign_targets: radius_map has 4 or 5 columns");
+  if (B == 0 || M == 0) return COMB_OK;           // no ground truth at all: the zero-filled outputs are the answer
   COMB_CHECK_ARG(R == 4 || group != nullptr, "comb_centerhead_assign_targets: 5 columns need the group tensor");
-  if (B == 0) return COMB_OK;
-  if (M == 0) return COMB_OK;                     // no ground truth at all: the zero-filled outputs are the answer
   COMB_CHECK_ARG(gt_boxes && npgt && cls_map && heatmap && ret_boxes && inds && mask && radius_map && gtab && gtab_off,
                  "comb_centerhead_assign_targets: null pointer");
   AssignArgs a;
