@@ -165,16 +165,20 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tr_kernel(ConvFwdArgs p) {
     const int ld = p.ld;
     // slab sl, this warp: global pieces (4 * sl + r) * NP + i; piece gp -> tap gp >> kLogPPT, channels 16 * (gp % kPPT)
     int idx[NP];
+    // (32-bit element offsets into the rulebook — K * ld < 2^31 is checked on the host — and one base per slab: the
+    // 64-bit tap * ld products of the first version were a third of the loop's instructions)
+    const int* nbr_q = p.nbr + (q * 32 + lane);
     auto load_idx = [&](int ti, int sl) {
-      const int row = ((int)blockIdx.x + ti * (int)gridDim.x) * kBM + q * 32 + lane;
+      const int tile_row = ((int)blockIdx.x + ti * (int)gridDim.x) * kBM;
       const int gp0 = (4 * sl + r) * NP;
-      const bool live = row < no && ti < my_tiles;
-      const int* src = p.nbr + row;
+      const int t0 = gp0 >> Cfg::kLogPPT, sub = gp0 & (Cfg::kPPT - 1);
+      const bool live = tile_row + q * 32 + lane < no && ti < my_tiles;
+      const int* src = nbr_q + (t0 * ld + tile_row);
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        const int tap = (gp0 + i) >> Cfg::kLogPPT;
+        const int dt = (sub + i) >> Cfg::kLogPPT;           // tap of piece i relative to t0 (compile-time at Cin = 16)
         idx[i] = -1;
-        if (tap < K && live) idx[i] = __ldg(src + (size_t)tap * ld);
+        if (t0 + dt < K && live) idx[i] = __ldg(src + dt * ld);
       }
     };
     int ti = 0, sl = 0;
@@ -350,6 +354,7 @@ template <int CIN, int COUT>
 int launch_tr(const ConvFwdArgs& p_in, cudaStream_t stream) {
   using Cfg = TrCfg<CIN, COUT>;
   ConvFwdArgs p = p_in;
+  COMB_CHECK_ARG((long long)p.K * p.ld < (1ll << 31), "comb_spconv_fwd_bf16: rulebook of %d x %d entries exceeds 32-bit offsets", p.K, p.ld);
   if (!Cfg::resident(p.K)) {
     set_error("comb_spconv_fwd_bf16: the row-per-thread kernel keeps the weight image in shared memory; %d x %d x %d does not fit", p.K, CIN, COUT);
     return COMB_EINVAL;
