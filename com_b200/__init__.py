@@ -66,7 +66,7 @@ def _hook_center_head(mod):
 
 def _hook_center_targets(mod):
     """curriculum_center_head.py:203-296, 431-473: target assignment and the curriculum groups on the device
-    (comb_centerhead_assign_targets / comb_centerhead_cluster_groups) for single-head configurations."""
+    (comb_centerhead_assign_targets / comb_centerhead_cluster_groups), the in-place relabelling of gt_boxes included."""
     from .pcdet_ops import center_targets
     cls = getattr(mod, "CurriculumCenterHead", None)
     if cls is None or getattr(cls.assign_targets, "_comb", False):

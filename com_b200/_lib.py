@@ -86,7 +86,7 @@ SIGNATURES = {
     "comb_comaug_valid_mask": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "comb_centerhead_assign_targets": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float,
                                                c_float, c_int, c_int, c_int, c_double, c_int, c_int, c_float, _P, _P, c_int,
-                                               c_int, _P, _P, _P, _P, _P, c_int, _P]),
+                                               c_int, _P, _P, _P, _P, _P, c_int, c_int, _P]),
     "comb_centerhead_cluster_groups": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P]),
     "comb_comloss_group_confidence": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "comb_comloss_reweight": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_double, c_double, c_double,

@@ -52,6 +52,8 @@ __device__ float gaussian_radius_f32(float height, float width, float ov_minus /
 
 struct AssignArgs {
   const float* gt;          // [B][M][C]; class id (1-based, 0 = padding row) in column C-1
+  float* gt_rw;             // the same tensor, written when relabel is set
+  int relabel;
   const float* npgt;        // [B][M] points inside each box
   const long long* group;   // [B][M] curriculum group, or NULL (radius_map then has 4 columns)
   const int* cls_map;       // [n_cls + 1]: global class id -> index inside this head, -1 = another head
@@ -79,6 +81,7 @@ struct AssignArgs {
 // one block per frame
 __global__ void __launch_bounds__(kTgtThreads) assign_targets_kernel(AssignArgs a) {
   __shared__ int sel[kMaxObjsCap];        // object index (row of gt) of the k-th object of this head
+  __shared__ int sel_cls[kMaxObjsCap];    // its class inside the head (read before the in-place relabelling)
   __shared__ int s_warp[kTgtThreads / 32];
   __shared__ int s_base;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -99,7 +102,16 @@ __global__ void __launch_bounds__(kTgtThreads) assign_targets_kernel(AssignArgs 
     int off = s_base;
     for (int w = 0; w < warp; ++w) off += s_warp[w];
     const int k = off + __popc(bal & ((1u << lane) - 1u));
-    if (in && k < a.max_objs) sel[k] = m;
+    int local_cls = -1;
+    if (in) local_cls = a.cls_map[(long long)gt[(size_t)m * a.C + a.C - 1]];
+    if (in && k < a.max_objs) {
+      sel[k] = m;
+      sel_cls[k] = local_cls;
+    }
+    // The reference relabels the boxes of this head IN PLACE in the caller's gt_boxes while it collects them
+    // (`temp_box[-1] = cur_class_names.index(name) + 1`, curriculum_center_head.py:252-254): later heads — and the
+    // caller — see the head-local ids.  Reproduced when asked for (multi-head configurations).
+    if (in && a.relabel) a.gt_rw[((size_t)b * a.M + m) * a.C + a.C - 1] = (float)(local_cls + 1);
     __syncthreads();
     if (tid == 0) {
       int t = s_base;
@@ -130,7 +142,7 @@ __global__ void __launch_bounds__(kTgtThreads) assign_targets_kernel(AssignArgs 
     const float rf = gaussian_radius_f32(dx, dy, a.ov_minus, a.ov_plus, a.a3, a.b3c, a.c3c, a.a3x4);
     int radius = (int)rf;                            // .int(): truncation
     if (radius < a.min_radius) radius = a.min_radius;
-    const int cls = a.cls_map[(long long)g[a.C - 1]];      // (gt[-1] - 1) of the head-local 1-based id
+    const int cls = sel_cls[k];                            // (gt[-1] - 1) of the head-local 1-based id
 
     // draw_gaussian_to_heatmap (centernet_utils.py:86-108): element-wise max with the Gaussian window
     {
@@ -302,7 +314,7 @@ extern "C" int comb_centerhead_assign_targets(const float* gt_boxes, const float
                                               double overlap, int min_radius, int filter_points, float min_points,
                                               const float* gtab, const int* gtab_off, int rmax, int Ch, float* heatmap,
                                               float* ret_boxes, long long* inds, float* mask, long long* radius_map,
-                                              int R, void* stream_) {
+                                              int R, int relabel_in_place, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   COMB_CHECK_ARG(B >= 0 && M >= 0 && C >= 8, "comb_centerhead_assign_targets: gt_boxes must be (B, M, >= 8)");
   COMB_CHECK_ARG(max_objs >= 1 && max_objs <= kMaxObjsCap, "comb_centerhead_assign_targets: NUM_MAX_OBJS %d outside [1,%d]",
@@ -313,7 +325,7 @@ extern "C" int comb_centerhead_assign_targets(const float* gt_boxes, const float
   COMB_CHECK_ARG(gt_boxes && npgt && cls_map && heatmap && ret_boxes && inds && mask && radius_map && gtab && gtab_off,
                  "comb_centerhead_assign_targets: null pointer");
   AssignArgs a;
-  a.gt = gt_boxes; a.npgt = npgt; a.group = group; a.cls_map = cls_map; a.n_cls = n_cls;
+  a.gt = gt_boxes; a.gt_rw = const_cast<float*>(gt_boxes); a.relabel = relabel_in_place; a.npgt = npgt; a.group = group; a.cls_map = cls_map; a.n_cls = n_cls;
   a.B = B; a.M = M; a.C = C;
   a.x0 = x0; a.y0 = y0; a.vx = vx; a.vy = vy; a.stride = stride;
   a.W = W; a.H = H; a.max_objs = max_objs;

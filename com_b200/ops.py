@@ -794,10 +794,11 @@ def _gaussian_tables(device):
 
 def centerhead_assign_targets(gt_boxes, npgt, group, cls_map, num_classes_head, feature_map_size, feature_map_stride,
                               point_cloud_range, voxel_size, num_max_objs=500, gaussian_overlap=0.1, min_radius=2,
-                              filter_points=False, min_points=1):
+                              filter_points=False, min_points=1, relabel_in_place=False):
     """assign_target_of_single_head for every frame of ONE separate head (comb_centerhead_assign_targets).
     gt_boxes (B,M,C) fp32 cuda, npgt (B,M), group (B,M) int64 or None, cls_map (n_cls+1,) int32: global class id ->
-    index inside the head or -1; feature_map_size = (W, H).
+    index inside the head or -1; feature_map_size = (W, H).  relabel_in_place: overwrite the class column of this head's
+    boxes in `gt_boxes` with the head-local id, as the reference does while it walks a head (the next head sees it).
     -> heatmap (B,Ch,H,W), ret_boxes (B,N,C), inds (B,N) int64, mask (B,N) fp32, radius_map (B,N,4|5) int64."""
     lib = _lib.load()
     _need(gt_boxes, torch.float32, "gt_boxes")
@@ -823,7 +824,8 @@ def centerhead_assign_targets(gt_boxes, npgt, group, cls_map, num_classes_head, 
             _p(gt_boxes), _p(npgt), _p(group), _p(cls_map), int(cls_map.numel()) - 1, B, M, C, f32(point_cloud_range[0]),
             f32(point_cloud_range[1]), f32(voxel_size[0]), f32(voxel_size[1]), f32(feature_map_stride), W, H, N,
             float(gaussian_overlap), int(min_radius), 1 if filter_points else 0, float(min_points), _p(gtab), _p(goff),
-            _GTAB_RMAX, int(num_classes_head), _p(heatmap), _p(ret_boxes), _p(inds), _p(mask), _p(radius_map), R, _stream()),
+            _GTAB_RMAX, int(num_classes_head), _p(heatmap), _p(ret_boxes), _p(inds), _p(mask), _p(radius_map), R,
+            1 if relabel_in_place else 0, _stream()),
             "comb_centerhead_assign_targets")
     return heatmap, ret_boxes, inds, mask, radius_map
 

@@ -20,11 +20,11 @@ def enabled():
 
 
 def supported_head(head, gt_boxes):
-    """Single separate head (the COM configurations): with several heads the reference relabels `gt_boxes[..., -1]` IN
-    PLACE while it walks the first head (curriculum_center_head.py:252-254), which the later heads then see; that
-    side effect is not reproduced, such heads keep the reference method."""
+    """CUDA fp32 contiguous gt_boxes (the reference relabels `gt_boxes[..., -1]` IN PLACE while it walks a head,
+    curriculum_center_head.py:252-254, and later heads see it: the kernel writes into the caller's tensor to reproduce
+    that, so it must not be handed a copy), NUM_MAX_OBJS <= 1024."""
     try:
-        return (enabled() and len(head.class_names_each_head) == 1 and gt_boxes.is_cuda and gt_boxes.dtype == torch.float32
+        return (enabled() and gt_boxes.is_cuda and gt_boxes.dtype == torch.float32 and gt_boxes.is_contiguous()
                 and int(head.model_cfg.TARGET_ASSIGNER_CONFIG.NUM_MAX_OBJS) <= 1024 and gt_boxes.shape[-1] >= 8)
     except AttributeError:
         return False
@@ -43,14 +43,15 @@ def assign_targets(head, gt_boxes, feature_map_size=None, npgt=None, true_object
     ret = {"heatmaps": [], "target_boxes": [], "inds": [], "masks": [], "heatmap_masks": [], "radius_map": [],
            "heatmap_mask": []}
     all_names = ["bg", *head.class_names]
-    gt = gt_boxes.contiguous()
+    gt = gt_boxes                                      # contiguous (supported_head): relabelled in place like the reference
     for cur_class_names in head.class_names_each_head:
         cls_map = torch.tensor([cur_class_names.index(n) if n in cur_class_names else -1 for n in all_names],
                                dtype=torch.int32, device=gt.device)
         heatmap, ret_boxes, inds, mask, radius_map = ops.centerhead_assign_targets(
             gt, npgt, true_object, cls_map, len(cur_class_names), feature_map_size, cfg.FEATURE_MAP_STRIDE,
             head.point_cloud_range, head.voxel_size, num_max_objs=cfg.NUM_MAX_OBJS, gaussian_overlap=cfg.GAUSSIAN_OVERLAP,
-            min_radius=cfg.MIN_RADIUS, filter_points=head.epoch <= head.epoch_thredhold, min_points=head.min_points)
+            min_radius=cfg.MIN_RADIUS, filter_points=head.epoch <= head.epoch_thredhold, min_points=head.min_points,
+            relabel_in_place=True)
         ret["heatmaps"].append(heatmap)
         ret["target_boxes"].append(ret_boxes)
         ret["inds"].append(inds)

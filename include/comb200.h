@@ -370,13 +370,15 @@ int comb_comaug_valid_mask(const float* iou1, const float* iou2, int S, int E, u
  *   EPOCH_THRED), gtab / gtab_off / rmax: Gaussian windows of radius 0..rmax built on the host with the reference's
  *   numpy formula (gtab_off[r] = offset of the (2r+1)^2 window).  Outputs must be ZERO-filled by the caller:
  *   heatmap [B,Ch,H,W], ret_boxes [B,max_objs,C], inds [B,max_objs] int64, mask [B,max_objs] fp32, radius_map
- *   [B,max_objs,R] int64 (class, x, y, radius[, group]). */
+ *   [B,max_objs,R] int64 (class, x, y, radius[, group]).  relabel_in_place = 1 reproduces the reference's side effect
+ *   (curriculum_center_head.py:252-254): the class column of this head's boxes in gt_boxes is overwritten with the
+ *   head-local 1-based id, which is what the NEXT head's call then reads (multi-head configurations). */
 int comb_centerhead_assign_targets(const float* gt_boxes, const float* npgt, const long long* group,
                                    const int* cls_map, int n_cls, int B, int M, int C, float x0, float y0, float vx,
                                    float vy, float stride, int W, int H, int max_objs, double overlap, int min_radius,
                                    int filter_points, float min_points, const float* gtab, const int* gtab_off,
                                    int rmax, int Ch, float* heatmap, float* ret_boxes, long long* inds, float* mask,
-                                   long long* radius_map, int R, void* stream);
+                                   long long* radius_map, int R, int relabel_in_place, void* stream);
 /* cluster(): curriculum group of each of n ground-truth boxes (gt_boxes [n,C]); the three attribute arrays are fp32. */
 int comb_centerhead_cluster_groups(const float* gt_boxes, int n, int C, const float* true_object,
                                    const float* occupancy_ratio, const float* facade_type, long long* group,

@@ -82,6 +82,31 @@ def test_cluster_and_assign_targets_vs_reference_methods(B, M, extra, max_objs, 
     assert g.shape == w.shape and torch.allclose(g, w, rtol=1e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("heads", [[["Vehicle"], ["Pedestrian", "Cyclist"]], [["Pedestrian", "Cyclist"], ["Vehicle"]]])
+def test_assign_targets_multi_head_relabels_gt_in_place_like_the_reference(heads):
+    """Several separate heads: the reference overwrites the class column of gt_boxes with the head-local id while it
+    walks a head (curriculum_center_head.py:252-254), so the NEXT head — and the caller — see relabelled boxes (with
+    the second head order pedestrians re-enter the Vehicle head as class 1).  Same targets, same mutated gt_boxes."""
+    E = ref_py.EasyDict
+    ch = ref_py.load("pcdet.models.dense_heads.curriculum_center_head")
+    head = fake_head(ch, E)
+    head.__dict__["class_names_each_head"] = heads
+    gt, npgt, to, occ, fac = (t.cuda() for t in scene(2, 130, 21))
+    grp = ops.centerhead_cluster_groups(gt, to, occ, fac)
+    gt_ref, gt_got = gt.clone(), gt.clone()
+    want = ch.CurriculumCenterHead.assign_targets.reference(head, gt_ref, feature_map_size=(188, 188), npgt=npgt, true_object=grp)
+    assert center_targets.supported_head(head, gt_got)
+    got = ch.CurriculumCenterHead.assign_targets(head, gt_got, feature_map_size=(188, 188), npgt=npgt, true_object=grp)
+    assert torch.equal(gt_got, gt_ref) and not torch.equal(gt_ref, gt)        # the side effect, reproduced
+    for key in ("heatmaps", "inds", "masks", "radius_map", "heatmap_mask"):
+        assert len(got[key]) == len(want[key]) == 2
+        for h in range(2):
+            assert got[key][h].shape == want[key][h].shape and torch.equal(got[key][h], want[key][h]), (key, h)
+    for h in range(2):
+        assert torch.allclose(got["target_boxes"][h], want["target_boxes"][h], rtol=1e-6, atol=1e-6)
+        assert float(want["masks"][h].sum()) > 5
+
+
 def test_assign_targets_point_filter_is_epoch_gated():
     """MIN_POINTS drops sparse boxes only while epoch <= EPOCH_THRED (curriculum_center_head.py:167-168)."""
     E = ref_py.EasyDict
