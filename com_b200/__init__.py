@@ -68,6 +68,18 @@ def _hook_center_targets(mod):
     """curriculum_center_head.py:203-296, 431-473: target assignment and the curriculum groups on the device
     (comb_centerhead_assign_targets / comb_centerhead_cluster_groups), the in-place relabelling of gt_boxes included."""
     from .pcdet_ops import center_targets
+    plain = getattr(mod, "CenterHead", None)
+    if plain is not None and not getattr(plain.assign_targets, "_comb", False):
+        ref_plain = plain.assign_targets
+
+        def assign_targets_plain(self, gt_boxes, feature_map_size=None, _ref=ref_plain, **kwargs):
+            if center_targets.supported_head(self, gt_boxes):
+                return center_targets.assign_targets_plain(self, gt_boxes, feature_map_size=feature_map_size, **kwargs)
+            return _ref(self, gt_boxes, feature_map_size=feature_map_size, **kwargs)
+
+        assign_targets_plain._comb = True
+        assign_targets_plain.reference = ref_plain
+        plain.assign_targets = assign_targets_plain
     cls = getattr(mod, "CurriculumCenterHead", None)
     if cls is None or getattr(cls.assign_targets, "_comb", False):
         return

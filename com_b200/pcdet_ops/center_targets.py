@@ -61,6 +61,28 @@ def assign_targets(head, gt_boxes, feature_map_size=None, npgt=None, true_object
     return ret
 
 
+def assign_targets_plain(head, gt_boxes, feature_map_size=None, **kwargs):
+    """Same arguments and return value as CenterHead.assign_targets (pcdet/models/dense_heads/center_head.py:161-220):
+    the assignment without the point-count filter and the group column; masks are int64 there."""
+    feature_map_size = feature_map_size[::-1]          # [H, W] -> [x, y]
+    cfg = head.model_cfg.TARGET_ASSIGNER_CONFIG
+    ret = {"heatmaps": [], "target_boxes": [], "inds": [], "masks": [], "heatmap_masks": []}
+    all_names = ["bg", *head.class_names]
+    npgt = torch.zeros(gt_boxes.shape[:-1], dtype=torch.float32, device=gt_boxes.device)
+    for cur_class_names in head.class_names_each_head:
+        cls_map = torch.tensor([cur_class_names.index(n) if n in cur_class_names else -1 for n in all_names],
+                               dtype=torch.int32, device=gt_boxes.device)
+        heatmap, ret_boxes, inds, mask, _ = ops.centerhead_assign_targets(
+            gt_boxes, npgt, None, cls_map, len(cur_class_names), feature_map_size, cfg.FEATURE_MAP_STRIDE,
+            head.point_cloud_range, head.voxel_size, num_max_objs=cfg.NUM_MAX_OBJS, gaussian_overlap=cfg.GAUSSIAN_OVERLAP,
+            min_radius=cfg.MIN_RADIUS, filter_points=False, relabel_in_place=True)
+        ret["heatmaps"].append(heatmap)
+        ret["target_boxes"].append(ret_boxes)
+        ret["inds"].append(inds)
+        ret["masks"].append(mask.long())
+    return ret
+
+
 def supported_loss(mod, pred, radius_map, mask):
     return (enabled() and pred.is_cuda and pred.dtype == torch.float32 and mask is not None and radius_map.shape[-1] >= 5
             and radius_map.dtype == torch.int64)

@@ -107,6 +107,28 @@ def test_assign_targets_multi_head_relabels_gt_in_place_like_the_reference(heads
         assert float(want["masks"][h].sum()) > 5
 
 
+@pytest.mark.parametrize("heads", [[list(NAMES)], [["Vehicle"], ["Pedestrian", "Cyclist"]]])
+def test_plain_center_head_assign_targets_vs_reference_method(heads):
+    """CenterHead.assign_targets (center_head.py:161-220, the head of the plain CenterPoint configurations): same
+    kernel without the point filter and the group column; masks are int64 there."""
+    E = ref_py.EasyDict
+    chm = ref_py.load("pcdet.models.dense_heads.center_head")
+    assert chm.CenterHead.assign_targets._comb
+    head = object.__new__(chm.CenterHead)
+    cfg = E(TARGET_ASSIGNER_CONFIG=E(FEATURE_MAP_STRIDE=8, NUM_MAX_OBJS=500, GAUSSIAN_OVERLAP=0.1, MIN_RADIUS=2))
+    head.__dict__.update(model_cfg=cfg, class_names=NAMES, class_names_each_head=heads, point_cloud_range=RANGE, voxel_size=VSIZE)
+    gt = scene(3, 160, 31, extra=2)[0].cuda()
+    gt_ref, gt_got = gt.clone(), gt.clone()
+    want = chm.CenterHead.assign_targets.reference(head, gt_ref, feature_map_size=(188, 188))
+    got = chm.CenterHead.assign_targets(head, gt_got, feature_map_size=(188, 188))
+    assert set(got) == set(want) and torch.equal(gt_got, gt_ref)
+    for h in range(len(heads)):
+        for key in ("heatmaps", "inds", "masks"):
+            assert got[key][h].dtype == want[key][h].dtype and torch.equal(got[key][h], want[key][h]), (key, h)
+        assert torch.allclose(got["target_boxes"][h], want["target_boxes"][h], rtol=1e-6, atol=1e-6)
+    assert got["masks"][0].dtype == torch.int64 and int(want["masks"][0].sum()) > 10
+
+
 def test_assign_targets_point_filter_is_epoch_gated():
     """MIN_POINTS drops sparse boxes only while epoch <= EPOCH_THRED (curriculum_center_head.py:167-168)."""
     E = ref_py.EasyDict
