@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tr_kernel(ConvFwdArgs p) {
         ++ti;
       }
       load_idx(ti, sl);
-      mbar_wait_warp(bars + kBarEmpty + 8 * slot, ((j >> 1) & 1u) ^ 1u);
+      mbar_wait(bars + kBarEmpty + 8 * slot, ((j >> 1) & 1u) ^ 1u);      // every lane polls: see mbar_wait_warp in tc_util.cuh
       tc_fence_after();
       const uint32_t t_dst = t_base + slot * Cfg::kSlotCols;
 #pragma unroll
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tr_kernel(ConvFwdArgs p) {
         rv[0] = __ldg(rp);
         rv[1] = __ldg(rp + 1);
       }
-      mbar_wait_sleep_warp(bars + kBarAccFull + 8 * a, (uint32_t)(ti >> 1) & 1u);
+      mbar_wait_sleep(bars + kBarAccFull + 8 * a, (uint32_t)(ti >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = ((uint32_t)(q * 32) << 16) + a * COUT;
       if (!(p.ablate & 8))

@@ -129,8 +129,8 @@ __device__ __forceinline__ void dbg_cta_time(long long* dbg, int slot) {   // pe
 // instruction suspends the warp in hardware for a bounded time), everything else backs off with nanosleep
 template <int PIPE>
 __device__ __forceinline__ void wait_bg(uint32_t bar, uint32_t parity) {
-  if (PIPE == 2) mbar_wait_warp(bar, parity);
-  else mbar_wait_sleep_warp(bar, parity);
+  if (PIPE == 2) mbar_wait(bar, parity);
+  else mbar_wait_sleep(bar, parity);
 }
 
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

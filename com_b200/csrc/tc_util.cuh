@@ -38,11 +38,12 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
         : "memory");
   }
 }
-// Whole-warp wait with ONE polling lane.  The barrier unit serves try_wait per thread, not per warp (r2
-// scripts/micro/mbar_bench.cu: 32 lanes polling a completed phase cost 41 cycles per round, and a CTA with 16 waiting
-// warps keeps 512 polls in flight: with nothing but its hand-shakes left, the 16-warp gather of the sparse-conv kernels
-// ran at ~1500 cycles per barrier round).  Lane 0 polls, __syncwarp releases the others (and orders their later
-// accesses after lane 0's acquire).
+// Whole-warp wait with ONE polling lane (lane 0 polls, __syncwarp releases the others).  Measured and NOT used by the
+// conv kernels: the barrier unit does serve try_wait per thread (scripts/micro/mbar_bench.cu: 32 lanes polling a
+// completed phase cost 41 cycles per round), but the divergent branch + __syncwarp makes ptxas re-materialise its uniform
+// registers after the reconvergence point (28 R2UR per gather iteration in conv_tr for the load descriptors alone);
+// same-box A/B, every lane polling against one: conv_ts 29.3 vs 31.6 us (16x16), 47.0 vs 49.3 (64x64), 28.5 vs 29.3
+// (128x128); conv_tr 23.0 vs 24.1 (16x16), 47.2 vs 46.2 (32x32).
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
   if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
   __syncwarp();
