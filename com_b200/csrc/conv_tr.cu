@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tr_kernel(ConvFwdArgs p) {
     int idx[NP];
     // (32-bit element offsets into the rulebook — K * ld < 2^31 is checked on the host — and one base per slab: the
     // 64-bit tap * ld products of the first version were a third of the loop's instructions; same-box A/B 24.0 vs 25.2 us
-    // at 16x16, 45.9 vs 48.8 at 32x32)
+    // at 16x16, 45.9 vs 48.8 at 32x32.  Cache hints measured the same way and rejected: L1::no_allocate on the rulebook
+    // loads 23.9 vs 23.2 us, plus L1::evict_last on the row loads 23.8)
     const int* nbr_q = p.nbr + (q * 32 + lane);
     auto load_idx = [&](int ti, int sl) {
       const int tile_row = ((int)blockIdx.x + ti * (int)gridDim.x) * kBM;
