@@ -192,7 +192,9 @@ __device__ __forceinline__ float iou_from_overlap(const BoxRec& a, const BoxRec&
 //      from tile to tile and is flushed once at the end.
 // (r1 history on the COMAug 10k x 10k case, 0.4 % of the pairs overlap: one thread per pair 1.55 ms — 12 % of the warps
 // held one near pair and ran the geometry for a single lane; per-tile queues 0.75 ms — every tile still paid one
-// round for its ~55 queued pairs.)
+// round for its ~55 queued pairs.  r2: clearing the output with a memset first and writing only the near pairs from
+// the kernel, with 32 rows per barrier round, is NOT faster — 0.547 vs 0.51 ms, bit-identical — so the zero stores are
+// not what bounds this kernel; what is left is the geometry rounds and their imbalance between blocks.)
 constexpr int kTB = 128, kPairsPerThread = 8, kRound = 256;
 constexpr int kQueueCap = kRound + 16 * kTB;      // a 16-row step adds at most 16 x 128 pairs to a remainder < 256
 
