@@ -769,26 +769,31 @@ _GTAB_RMAX = 48
 _gtab_cache = {}
 
 
-def _gaussian_tables(device):
+def _gaussian_tables_host():
     """Gaussian windows of radius 0.._GTAB_RMAX, built with the formula of centernet_utils.gaussian2D
     (pcdet/models/model_utils/centernet_utils.py:78-84: float64 exp, eps cut, cast to fp32) so that the device heat maps
-    carry the reference's values bit for bit."""
+    carry the reference's values bit for bit.  -> (list of (2r+1, 2r+1) fp32 arrays, offsets int32[rmax+2])."""
+    tabs, offs, o = [], [], 0
+    for r in range(_GTAB_RMAX + 1):
+        d = 2 * r + 1
+        m = n = (d - 1.) / 2.
+        y, x = np.ogrid[-m:m + 1, -n:n + 1]
+        sigma = d / 6
+        h = np.exp(-(x * x + y * y) / (2 * sigma * sigma))
+        h[h < np.finfo(h.dtype).eps * h.max()] = 0
+        tabs.append(h.astype(np.float32))
+        offs.append(o)
+        o += d * d
+    offs.append(o)
+    return tabs, np.asarray(offs, dtype=np.int32)
+
+
+def _gaussian_tables(device):
     key = str(device)
     if key not in _gtab_cache:
-        import numpy as np
-        tabs, offs, o = [], [], 0
-        for r in range(_GTAB_RMAX + 1):
-            d = 2 * r + 1
-            m = n = (d - 1.) / 2.
-            y, x = np.ogrid[-m:m + 1, -n:n + 1]
-            sigma = d / 6
-            h = np.exp(-(x * x + y * y) / (2 * sigma * sigma))
-            h[h < np.finfo(h.dtype).eps * h.max()] = 0
-            tabs.append(torch.from_numpy(h).float().reshape(-1))
-            offs.append(o)
-            o += d * d
-        offs.append(o)
-        _gtab_cache[key] = (torch.cat(tabs).to(device), torch.tensor(offs, dtype=torch.int32, device=device))
+        tabs, offs = _gaussian_tables_host()
+        flat = np.concatenate([t.reshape(-1) for t in tabs])
+        _gtab_cache[key] = (torch.from_numpy(flat).to(device), torch.from_numpy(offs).to(device))
     return _gtab_cache[key]
 
 

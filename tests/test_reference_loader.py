@@ -73,3 +73,46 @@ def test_bytecode_build_loads_without_source_tree():
     env = dict(os.environ, COM_REFERENCE="/nonexistent")
     r = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+def test_round2_hooks_attach_and_leave_cpu_tensors_to_the_reference():
+    """The §8(f) hooks: every patched method keeps the reference's own function as `.reference`, and inputs the device
+    kernels do not cover (CPU tensors here) run the reference method unchanged — the drop-in never silently computes
+    on another path."""
+    import torch
+    E = ref_py.EasyDict
+    ch = ref_py.load("pcdet.models.dense_heads.curriculum_center_head")
+    chp = ref_py.load("pcdet.models.dense_heads.center_head")
+    lu = ref_py.load("pcdet.utils.loss_utils")
+    hc = ref_py.load("pcdet.models.backbones_2d.map_to_bev.height_compression")
+    bev = ref_py.load("pcdet.models.backbones_2d.base_bev_backbone")
+    for fn in (ch.CurriculumCenterHead.assign_targets, ch.CurriculumCenterHead.cluster,
+               ch.CurriculumCenterHead.generate_predicted_boxes, chp.CenterHead.assign_targets,
+               chp.CenterHead.generate_predicted_boxes, lu.FocalLossCenterCurriculum.neg_loss,
+               hc.HeightCompression.forward, bev.BaseBEVBackbone.forward):
+        assert fn._comb and callable(fn.reference) and not getattr(fn.reference, "_comb", False)
+    from com_b200.pcdet_ops import center_targets
+    head = object.__new__(ch.CurriculumCenterHead)
+    cfg = E(TARGET_ASSIGNER_CONFIG=E(FEATURE_MAP_STRIDE=8, NUM_MAX_OBJS=500, GAUSSIAN_OVERLAP=0.1, MIN_RADIUS=2))
+    head.__dict__.update(model_cfg=cfg, class_names=["Vehicle", "Pedestrian", "Cyclist"],
+                         class_names_each_head=[["Vehicle", "Pedestrian", "Cyclist"]],
+                         point_cloud_range=np.array([-75.2, -75.2, -2, 75.2, 75.2, 4], dtype=np.float32),
+                         voxel_size=[0.1, 0.1, 0.15], epoch=0, epoch_thredhold=100, min_points=1)
+    gt = torch.zeros((1, 4, 8))
+    gt[0, :3] = torch.tensor([[10.0, 5.0, 0.0, 4.5, 2.0, 1.6, 0.3, 1.0], [-20.0, 7.0, 0.0, 0.9, 0.8, 1.7, 1.0, 2.0],
+                              [30.0, -40.0, 0.5, 1.8, 0.8, 1.7, -2.0, 3.0]])
+    assert not center_targets.supported_head(head, gt)                    # CPU tensor: the reference method runs
+    npgt = torch.full((1, 4), 9.0)
+    grp = ch.CurriculumCenterHead.cluster(head, gt.clone(), torch.ones((1, 4)), torch.rand((1, 4)), torch.zeros((1, 4)))
+    out = ch.CurriculumCenterHead.assign_targets(head, gt.clone(), feature_map_size=(188, 188), npgt=npgt, true_object=grp)
+    assert float(out["masks"][0].sum()) == 3.0 and float(out["heatmaps"][0].max()) == 1.0
+    assert out["radius_map"][0].shape == (1, 500, 5)
+    # the Gaussian table the device kernels read is the reference's own formula, bit for bit
+    cu = ref_py.load("pcdet.models.model_utils.centernet_utils")
+    from com_b200 import ops
+    tabs, offs = ops._gaussian_tables_host()
+    assert len(tabs) == ops._GTAB_RMAX + 1 and int(offs[-1]) == sum((2 * r + 1) ** 2 for r in range(len(tabs)))
+    for r, tab in enumerate(tabs):
+        d = 2 * r + 1
+        want = torch.from_numpy(cu.gaussian2D((d, d), sigma=d / 6)).float().numpy()
+        assert tab.dtype == np.float32 and np.array_equal(tab, want), r
