@@ -81,6 +81,9 @@ SIGNATURES = {
     "comb_centerhead_decode_nms": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
                                            c_float, c_float, _PF, c_float, _P, c_float, c_int, c_int, _P, _P, _P, _P, _P,
                                            c_size_t, _P]),
+    "comb_centerhead_decode_nms_vel": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+                                               c_float, c_float, c_float, _PF, c_float, _P, c_float, c_int, c_int, _P, _P,
+                                               _P, _P, _P, c_size_t, _P]),
     "comb_dense_scatter_nhwc_bf16": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "comb_dense_gather_nhwc": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     "comb_comaug_valid_mask": (c_int, [_P, _P, c_int, c_int, _P, _P]),

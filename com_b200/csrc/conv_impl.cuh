@@ -30,6 +30,7 @@ struct ConvFwdArgs {
   int ni = 4;       // conv_ts: index-tile ring depth (set by launch_ts)
   int nb = 0;       // conv_ts: streamed-weight stages (set by launch_ts)
   int sc = 2;       // conv_ts: chunks of each row tile per A stage (set by launch_ts)
+  int split = 1;    // conv_ts: single-tile passes split their K range over the two halves of the pipeline (COMB_TS_SPLIT=0: r1 behaviour)
   int ablate = 0;   // conv_ts: COMB_TS_ABLATE bit mask — pipeline pieces switched off for timing experiments (results are garbage)
 };
 

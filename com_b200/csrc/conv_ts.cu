@@ -172,6 +172,16 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
   const int NS = (512 - Cfg::d_cols(K)) / (int)stage_cols;     // A stages
   const uint32_t colA = (uint32_t)Cfg::d_cols(K);
   const int nst = (nchunks + SC - 1) / SC;           // stages per super-tile (the last one may be partial)
+  // Single-tile passes (the split last wave below, or an odd tile at the end) used to leave the second half of the
+  // pipeline idle: 8 of the 16 gather warps, one of the two MMA threads.  At level 4 of the bench frames (101 row tiles
+  // on 148 SMs) EVERY pass is such a pass.  With p.split the idle half takes the UPPER half of the tile's stages
+  // (K split inside the CTA): gather groups 1 and 3 read the same index tile, MMA thread 1 accumulates stages
+  // [nst_p, nst) into the second accumulator, the streamed-weight ring carries the two stage sequences interleaved, and
+  // the epilogue adds the two accumulators (fixed order: deterministic).
+  // r2 A/B on the bench frames, same box, two runs each (profiles/r2_bench_split{0,1}.json): 64x64 67.9 -> 65.1 us per
+  // launch (its last wave is made of single-tile passes), step 1.0767 -> 1.0700 ms.  Level 4 does NOT gain: its dense-K
+  // row count is 246 tiles, i.e. 123 full two-tile passes, not 101 single ones as first assumed from the FLOP count.
+  const bool split_ok = PIPE != 1 && p.split != 0 && nst >= 2;
 
   // shared memory map (1024-byte aligned): [barriers 1 KB] [weights: resident image | NB streamed 2-chunk stages]
   // [index tiles NI x kpad x 128]
@@ -399,14 +409,23 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       // per pass: this warp's tile, its index buffer (waited for once), whether the tile exists
       const int n = (it << lT) + t;                    // tile sequence number of this CTA
       const int buf = n & (NI - 1);
-      const bool absent = t == 1 && absent_of(it);
-      const uint32_t idx_tile = idx_base + (uint32_t)buf * idx_buf_bytes;
+      const bool single = absent_of(it);
+      const bool split = split_ok && single;           // single-tile pass: my half of the warps takes half of its stages
+      const bool absent = t == 1 && single && !split;
+      const int nst_p = split ? (nst + 1) >> 1 : nst;  // stage steps of this pass
+      const int st_off = split && t == 1 ? nst_p : 0;  // first stage of my half
+      uint32_t idx_tile = idx_base + (uint32_t)buf * idx_buf_bytes;
       wait_bg<PIPE>(bars + kBarIdx + 8 * buf, (uint32_t)(n >> lNI) & 1u);   // also for an absent tile: its fill must have landed before the buffer is handed back
-      for (int st = 0; st < nst; ++st, ++gst) {
+      if (split && t == 1) {                           // the rows are tile 0's: read ITS index tile
+        const int n0 = n - 1, buf0 = n0 & (NI - 1);
+        wait_bg<PIPE>(bars + kBarIdx + 8 * buf0, (uint32_t)(n0 >> lNI) & 1u);
+        idx_tile = idx_base + (uint32_t)buf0 * idx_buf_bytes;
+      }
+      for (int st = 0; st < nst_p; ++st, ++gst) {
         // this group's chunks of the stage: offsets hc = grp>>1, grp>>1 + 2, ... < SC inside the stage (tile t = grp & 1)
         bool waited = false;
         for (int hc = grp >> 1; hc < SC; hc += 2) {
-          const int c = SC * st + hc;
+          const int c = SC * (st + st_off) + hc;
           const bool have = c < nchunks && !absent;
           uint4 v[2][2][2];     // [16-lane half][row, row+8][piece]
           if (TRACE && tr) dbg_stamp(p.dbg, gst, 2);
@@ -464,6 +483,8 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
     const int q = warp & 3;
     const int ntile_seq = my_super << lT;
     for (int n = 0; n < ntile_seq; ++n) {
+      const bool split = split_ok && absent_of(n >> lT);
+      if (split && (n & 1)) continue;                  // the second accumulator of a split pass is added to the first below
       const int tile = tile_of(n);
       const int a = n & (ND - 1);
       const int row = tile * kBM + q * 32 + lane;
@@ -475,6 +496,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
         rv[1] = __ldg(rp + 1);
       }
       wait_bg<PIPE>(bars + kBarTFull + 8 * a, (uint32_t)(n / ND) & 1u);
+      if (split) wait_bg<PIPE>(bars + kBarTFull + 8 * (a + 1), (uint32_t)((n + 1) / ND) & 1u);   // n even, ND even: a + 1 < ND
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * COUT;
       if (!(p.ablate & 8))
@@ -488,6 +510,16 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
           rn[1] = __ldg(rp + (c0 + 16) / 8 + 1);
         }
         tmem_ld_wait();
+        if (split) {
+          // upper-half partial sums from the second accumulator.  tcgen05.ld is .sync.aligned: every lane of the warp
+          // must execute it, so it stays OUTSIDE the per-row `live` branch (a partially live last tile hung the kernel
+          // when it sat inside)
+          uint32_t w2[16];
+          tmem_ld16(taddr + COUT + c0, w2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w2[i]));
+        }
         if (live) {
           float f[16];
 #pragma unroll
@@ -537,7 +569,10 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars + kBarTEmpty + 8 * a);
+      if (lane == 0) {
+        mbar_arrive(bars + kBarTEmpty + 8 * a);
+        if (split) mbar_arrive(bars + kBarTEmpty + 8 * (a + 1));
+      }
       if (TRACE && warp == kEpiWarp0 && lane == 0) dbg_stamp(p.dbg, n, 5);
     }
   } else if (warp == kMmaWarp || warp == kMmaWarp2) {
@@ -558,20 +593,34 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       uint32_t ph = 0, bph = 0;
       bool ready = false;
       if (bres) mbar_wait(bars + kBarB, 0);
+      auto ring_adv = [&](int& b, uint32_t& phs) {
+        if (++b == NB) { b = 0; phs ^= 1u; }
+      };
+      auto last_pass_of = [&](int it) -> bool { return it == my_super - 1; };
       // per pass: my tile's accumulator and whether the tile exists; per stage only ring arithmetic (the loop nest keeps
       // the live state of this thread small: its issue loop is the critical path of the kernel)
       for (int it = 0; it < my_super; ++it) {
         const int n = (it << lT) + my_t;              // tile sequence number of my tile in this pass
-        const bool absent = my_t == 1 && absent_of(it);   // single-tile pass
+        const bool single = absent_of(it);            // single-tile pass
+        const bool split = split_ok && single;        // ... whose upper stages are mine (my_t == 1), see split_ok
+        const bool absent = my_t == 1 && single && !split;
+        const int nst_p = split ? (nst + 1) >> 1 : nst;
+        const int st_off = split && my_t == 1 ? nst_p : 0;
+        const bool split_nx = !last_pass_of(it) && split_ok && absent_of(it + 1);
         const uint32_t acc = (uint32_t)(n & (ND - 1));
         const uint32_t tmem_d = tmem_base + acc * COUT;
         const uint32_t acc_ph = (uint32_t)(n / ND) & 1u;
         const bool last_pass = it == my_super - 1;
-        for (int st = 0; st < nst; ++st, ++gst) {
+        for (int st = 0; st < nst_p; ++st, ++gst) {
           if (TRACE && my_t == 0) dbg_stamp(p.dbg, gst, 6);
+          // streamed weights: (bs, bph) is the ring entry of tile 0's chunks of this stage; in a split pass the entry
+          // behind it carries the chunks of the upper half (mine if my_t == 1) and a stage consumes two entries
+          int mb = bs;
+          uint32_t mph = bph;
+          if (split && my_t == 1) ring_adv(mb, mph);
           if (!ready) {
             if (st == 0) mbar_wait(bars + kBarTEmpty + 8 * acc, acc_ph ^ 1u);
-            if (!bres) mbar_wait(bars + kBarBFull + 8 * bs, bph);
+            if (!bres) mbar_wait(bars + kBarBFull + 8 * mb, mph);
             mbar_wait(bars + kBarFull + 8 * s, ph);
           }
           if (TRACE && my_t == 0) dbg_stamp(p.dbg, gst, 0);
@@ -579,22 +628,27 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
           // ring positions of the next stage
           const int s2 = s + 1 == NS ? 0 : s + 1;
           const uint32_t ph2 = s + 1 == NS ? ph ^ 1u : ph;
-          const int bs2 = bs + 1 == NB ? 0 : bs + 1;
-          const uint32_t bph2 = bs + 1 == NB ? bph ^ 1u : bph;
-          const bool last_st = st == nst - 1;
+          const bool last_st = st == nst_p - 1;
+          int bs2 = bs;
+          uint32_t bph2 = bph;
+          ring_adv(bs2, bph2);
+          if (split) ring_adv(bs2, bph2);
+          int mb2 = bs2;                                // my entry of the NEXT stage (which may open the next pass)
+          uint32_t mph2 = bph2;
+          if ((last_st ? split_nx : split) && my_t == 1) ring_adv(mb2, mph2);
           const uint32_t a_stage = tmem_base + colA + (uint32_t)s * stage_cols + (uint32_t)(my_t * 32);
           for (int h = 0; h < SC; ++h) {
-            const int c = SC * st + h;                  // my chunk of the stage: slot 2*h + my_t
+            const int c = SC * (st + st_off) + h;       // my chunk of the stage: slot 2*h + my_t
             if (c < nchunks && !absent && !(AB & 1)) {
               const uint32_t tmem_a = a_stage + (uint32_t)(h * 64);
-              const uint64_t bdesc = make_desc_sw128(w_base + (uint32_t)(bres ? c : bs * SC + h) * Cfg::kBBytes);
+              const uint64_t bdesc = make_desc_sw128(w_base + (uint32_t)(bres ? c : mb * SC + h) * Cfg::kBBytes);
 #pragma unroll
               for (int kk = 0; kk < kChunkK / 16; ++kk)
-                umma_bf16_ts(tmem_d, tmem_a + 8 * kk, bdesc + 2 * kk, idesc, (c | kk) != 0 ? 1u : 0u);
+                umma_bf16_ts(tmem_d, tmem_a + 8 * kk, bdesc + 2 * kk, idesc, (st | h | kk) != 0 ? 1u : 0u);
             }
             if (h == 0) {   // probe the next stage while the other chunks of this one are still to be issued
               ready = !(last_pass && last_st) && !(AB & 32) && mbar_test(bars + kBarFull + 8 * s2, ph2);
-              if (!bres) ready = ready && mbar_test(bars + kBarBFull + 8 * bs2, bph2);
+              if (!bres) ready = ready && mbar_test(bars + kBarBFull + 8 * mb2, mph2);
               if (last_st) {
                 const int n2 = n + T;
                 ready = ready && mbar_test(bars + kBarTEmpty + 8 * (n2 & (ND - 1)), ((uint32_t)(n2 / ND) & 1u) ^ 1u);
@@ -602,7 +656,23 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
             }
           }
           umma_commit(bars + kBarEmpty + 8 * s);
-          if (!bres) umma_commit(bars + kBarBEmpty + 8 * bs);
+          if (!bres) {
+            // Every ring entry expects two arrivals.  In a split pass an entry has ONE reader; by default both threads
+            // still commit on both entries of the stage (an entry is then handed back when the MMAs of both threads up to
+            // this stage have retired — conservative, and the two-committers-per-barrier pattern of the normal passes);
+            // p.split & 2: the reader commits twice on its own entry instead.
+            if (!split) {
+              umma_commit(bars + kBarBEmpty + 8 * mb);
+            } else if (p.split & 2) {
+              umma_commit(bars + kBarBEmpty + 8 * mb);
+              umma_commit(bars + kBarBEmpty + 8 * mb);
+            } else {
+              int ob = bs;                                   // the other entry of the stage
+              if (my_t == 0) { uint32_t dummy = 0; ring_adv(ob, dummy); }
+              umma_commit(bars + kBarBEmpty + 8 * mb);
+              umma_commit(bars + kBarBEmpty + 8 * ob);
+            }
+          }
           if (last_st) umma_commit(bars + kBarTFull + 8 * acc);
           if (TRACE && my_t == 0) dbg_stamp(p.dbg, gst, 1);
           s = s2;
@@ -652,15 +722,25 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       // one SC-chunk weight stage per A stage (a stage is chunks SC*st .. SC*st+SC-1 for both row tiles)
       int bs = 0;
       uint32_t bph = 0;
-      for (int it = 0; it < my_super; ++it)
-        for (int st = 0; st < nst; ++st) {
-          const int c0 = SC * st;
-          const uint32_t bytes = (uint32_t)(nchunks - c0 < SC ? nchunks - c0 : SC) * Cfg::kBBytes;
+      for (int it = 0; it < my_super; ++it) {
+        // a split pass (see split_ok) interleaves the stage sequences of its two halves: entry 2*st = stage st,
+        // entry 2*st + 1 = stage nst_p + st (possibly past the end: an empty entry, completed by a plain arrive)
+        const bool split = split_ok && absent_of(it);
+        const int nst_p = split ? (nst + 1) >> 1 : nst;
+        for (int e = 0; e < (split ? 2 * nst_p : nst_p); ++e) {
+          const int c0 = SC * (split ? (e >> 1) + (e & 1) * nst_p : e);
+          const int left = nchunks - c0;
+          const uint32_t bytes = (uint32_t)(left < SC ? (left > 0 ? left : 0) : SC) * Cfg::kBBytes;
           mbar_wait(bars + kBarBEmpty + 8 * bs, bph ^ 1u);
-          mbar_arrive_expect_tx(bars + kBarBFull + 8 * bs, bytes);
-          bulk_copy_g2s(w_base + bs * SC * Cfg::kBBytes, p.wpacked + (size_t)c0 * Cfg::kBBytes, bytes, bars + kBarBFull + 8 * bs);
+          if (bytes != 0) {
+            mbar_arrive_expect_tx(bars + kBarBFull + 8 * bs, bytes);
+            bulk_copy_g2s(w_base + bs * SC * Cfg::kBBytes, p.wpacked + (size_t)c0 * Cfg::kBBytes, bytes, bars + kBarBFull + 8 * bs);
+          } else {
+            mbar_arrive(bars + kBarBFull + 8 * bs);
+          }
           if (++bs == NB) { bs = 0; bph ^= 1u; }
         }
+      }
     }
   }
 
@@ -762,8 +842,12 @@ int launch_ts(const ConvFwdArgs& p_in, cudaStream_t stream) {
     set_error("comb_spconv_fwd_bf16: shared memory %zu exceeds the per-CTA limit", smem);
     return COMB_EINVAL;
   }
-  const int nsuper = cdiv(cdiv(p.no_max, kBM), Cfg::tiles_per_pass(p.K));
-  const int grid = nsuper < sm_count() ? nsuper : sm_count();
+  // one CTA per ROW TILE up to the SM count (not per super-tile): the kernel turns a last wave of r <= grid/2 super-tiles
+  // into 2r single-tile passes, which needs the CTAs to exist
+  static const int split_env = env_int("COMB_TS_SPLIT", 1);
+  p.split = split_env;
+  const int ntiles_max = cdiv(p.no_max, kBM);
+  const int grid = ntiles_max < sm_count() ? ntiles_max : sm_count();
   if (p.dbg != nullptr) COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, true, 0>, grid, kThreads, smem, stream, p));   // pipeline trace build
 #ifdef COMB_TS_EXPERIMENTS     // the two measured-and-rejected gather variants (software-pipelined gather, sleep-free waits): built on demand only
   else if (ts_pipe() == 1) COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, false, 1>, grid, kThreads, smem, stream, p));

@@ -31,12 +31,14 @@ __device__ __forceinline__ float key_to_float(unsigned k) {
 
 struct DecodeArgs {
   const float *hm, *center, *center_z, *dim, *rot;
+  const float* vel;  // [B][2][H][W] or null (heads with 'vel' in HEAD_ORDER: nuScenes, centerpoint_4frames)
   int B, C, H, W, K;
   float stride, vx, vy, rx, ry;
   float lim[6];
   float score_thresh;
   const int* label_map;
   float* boxes;      // [B][K][7]   masked candidates, score-sorted, compacted
+  float* cvel;       // [B][K][2]   their velocities (vel != null)
   float* scores;     // [B][K]
   int* labels;       // [B][K]
   int* counts;       // [B]
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(kDecThreads) centerhead_topk_decode_kernel(Dec
 
   // ---- decode + mask (thread t = candidate t of the sorted list)
   bool ok = false;
-  float box[7], score = 0.f;
+  float box[7], score = 0.f, v0 = 0.f, v1 = 0.f;
   int label = 0;
   if (tid < K) {
     const unsigned long long c = cand[tid];
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(kDecThreads) centerhead_topk_decode_kernel(Dec
     box[4] = expf(__ldg(a.dim + f3 + HW + pos));
     box[5] = expf(__ldg(a.dim + f3 + 2 * HW + pos));
     box[6] = atan2f(rs, rc);
+    if (a.vel != nullptr) { v0 = __ldg(a.vel + f2 + pos); v1 = __ldg(a.vel + f2 + HW + pos); }
     ok = box[0] >= a.lim[0] && box[1] >= a.lim[1] && box[2] >= a.lim[2] && box[0] <= a.lim[3] && box[1] <= a.lim[4] &&
          box[2] <= a.lim[5] && score > a.score_thresh;
     label = (a.label_map != nullptr ? __ldg(a.label_map + cls) : cls) + 1;
@@ -197,6 +200,7 @@ __global__ void __launch_bounds__(kDecThreads) centerhead_topk_decode_kernel(Dec
     for (int q = 0; q < 7; ++q) bo[q] = box[q];
     a.scores[(size_t)b * a.K + o] = score;
     a.labels[(size_t)b * a.K + o] = label;
+    if (a.vel != nullptr) { a.cvel[((size_t)b * a.K + o) * 2] = v0; a.cvel[((size_t)b * a.K + o) * 2 + 1] = v1; }
   }
 }
 
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(kDecThreads) centerhead_topk_decode_kernel(Dec
 __global__ void __launch_bounds__(256) centerhead_gather_keep_kernel(const float* __restrict__ boxes,
                                                                       const float* __restrict__ scores,
                                                                       const int* __restrict__ labels,
+                                                                      const float* __restrict__ cvel,
                                                                       const long long* __restrict__ keep,
                                                                       const int* __restrict__ num_keep, int K, int post_max,
                                                                       float* __restrict__ out_boxes,
@@ -216,7 +221,11 @@ __global__ void __launch_bounds__(256) centerhead_gather_keep_kernel(const float
   if (threadIdx.x == 0) out_counts[b] = n;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     const int src = (int)keep[(size_t)b * K + j];
-    for (int q = 0; q < 7; ++q) out_boxes[((size_t)b * K + j) * 7 + q] = boxes[((size_t)b * K + src) * 7 + q];
+    // (n, 7) boxes, or (n, 9) with the two velocity columns behind the heading (decode_bbox_from_heatmap's cat order)
+    const int cols = cvel != nullptr ? 9 : 7;
+    float* ob = out_boxes + ((size_t)b * K + j) * cols;
+    for (int q = 0; q < 7; ++q) ob[q] = boxes[((size_t)b * K + src) * 7 + q];
+    if (cvel != nullptr) { ob[7] = cvel[((size_t)b * K + src) * 2]; ob[8] = cvel[((size_t)b * K + src) * 2 + 1]; }
     out_scores[(size_t)b * K + j] = scores[(size_t)b * K + src];
     out_labels[(size_t)b * K + j] = labels[(size_t)b * K + src];
   }
@@ -234,13 +243,13 @@ extern "C" int comb_nms_dev(const float* boxes, const float* trig, int n_max, co
 
 extern "C" size_t comb_centerhead_workspace_bytes(int B, int K) {
   if (B < 1 || K < 1 || K > kDecMaxK) return 0;
-  const size_t per = align_up((size_t)K * 7 * 4, 256) + 2 * align_up((size_t)K * 4, 256) + align_up((size_t)K * 8, 256) +
+  const size_t per = align_up((size_t)K * 7 * 4, 256) + 2 * align_up((size_t)K * 4, 256) + 2 * align_up((size_t)K * 8, 256) +
                      comb_nms_workspace_bytes(K);
   return (size_t)B * per + align_up((size_t)2 * B * 4, 256);
 }
 
-extern "C" int comb_centerhead_decode_nms(const float* hm, const float* center, const float* center_z, const float* dim,
-                                          const float* rot, int B, int C, int H, int W, int K, float stride, float vx,
+extern "C" int comb_centerhead_decode_nms_vel(const float* hm, const float* center, const float* center_z,
+                                              const float* dim, const float* rot, const float* vel, int B, int C, int H, int W, int K, float stride, float vx,
                                           float vy, float rx, float ry, const float* limit_range, float score_thresh,
                                           const int* label_map, float nms_thresh, int nms_pre_max, int nms_post_max,
                                           float* out_boxes, float* out_scores, int* out_labels, int* out_counts,
@@ -259,13 +268,15 @@ extern "C" int comb_centerhead_decode_nms(const float* hm, const float* center, 
   float* c_scores = (float*)w;       w += (size_t)B * align_up((size_t)K * 4, 256);
   int* c_labels = (int*)w;           w += (size_t)B * align_up((size_t)K * 4, 256);
   long long* keep = (long long*)w;   w += (size_t)B * align_up((size_t)K * 8, 256);
+  float* c_vel = (float*)w;          w += (size_t)B * align_up((size_t)K * 8, 256);
   int* c_counts = (int*)w;
   int* num_keep = c_counts + B;      w += align_up((size_t)2 * B * 4, 256);
   uint8_t* nms_ws = w;
   // the per-frame strides above are K elements only when K*4 etc. are multiples of 256: use plain K strides instead
   // (simpler addressing in the kernels) — the workspace formula over-allocates, which is harmless
   DecodeArgs a;
-  a.hm = hm; a.center = center; a.center_z = center_z; a.dim = dim; a.rot = rot;
+  a.hm = hm; a.center = center; a.center_z = center_z; a.dim = dim; a.rot = rot; a.vel = vel;
+  a.cvel = c_vel;
   a.B = B; a.C = C; a.H = H; a.W = W; a.K = K;
   a.stride = stride; a.vx = vx; a.vy = vy; a.rx = rx; a.ry = ry;
   for (int i = 0; i < 6; ++i) a.lim[i] = limit_range[i];
@@ -281,8 +292,19 @@ extern "C" int comb_centerhead_decode_nms(const float* hm, const float* center, 
                           num_keep + b, nms_ws + (size_t)b * nms_bytes, nms_bytes, stream_);
     if (rc != COMB_OK) return rc;
   }
-  centerhead_gather_keep_kernel<<<B, 256, 0, stream>>>(c_boxes, c_scores, c_labels, keep, num_keep, K, nms_post_max,
+  centerhead_gather_keep_kernel<<<B, 256, 0, stream>>>(c_boxes, c_scores, c_labels, vel != nullptr ? c_vel : nullptr, keep, num_keep, K, nms_post_max,
                                                         out_boxes, out_scores, out_labels, out_counts);
   COMB_LAUNCH_CHECK();
   return COMB_OK;
+}
+
+extern "C" int comb_centerhead_decode_nms(const float* hm, const float* center, const float* center_z, const float* dim,
+                                          const float* rot, int B, int C, int H, int W, int K, float stride, float vx,
+                                          float vy, float rx, float ry, const float* limit_range, float score_thresh,
+                                          const int* label_map, float nms_thresh, int nms_pre_max, int nms_post_max,
+                                          float* out_boxes, float* out_scores, int* out_labels, int* out_counts,
+                                          void* workspace, size_t workspace_bytes, void* stream_) {
+  return comb_centerhead_decode_nms_vel(hm, center, center_z, dim, rot, nullptr, B, C, H, W, K, stride, vx, vy, rx, ry,
+                                        limit_range, score_thresh, label_map, nms_thresh, nms_pre_max, nms_post_max,
+                                        out_boxes, out_scores, out_labels, out_counts, workspace, workspace_bytes, stream_);
 }

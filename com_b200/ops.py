@@ -734,18 +734,20 @@ def nms(boxes, thresh, rotated=True, flavour="gpu", trig=None):
 
 
 def centerhead_decode_nms(hm, center, center_z, dim, rot, K, feature_map_stride, voxel_size, point_cloud_range,
-                          post_center_limit_range, score_thresh, nms_thresh, nms_pre_max, nms_post_max, label_map=None):
-    """One separate head of CenterHead.generate_predicted_boxes on the device (comb_centerhead_decode_nms).
+                          post_center_limit_range, score_thresh, nms_thresh, nms_pre_max, nms_post_max, label_map=None,
+                          vel=None):
+    """One separate head of CenterHead.generate_predicted_boxes on the device (comb_centerhead_decode_nms[_vel]).
     hm / dim are the RAW head outputs.  -> (boxes (B,K,7), scores (B,K), labels (B,K) int32 1-based, counts (B,) int32),
-    capacity-sized with the per-frame counts on the device."""
+    capacity-sized with the per-frame counts on the device; with a velocity head (vel (B,2,H,W)) boxes are (B,K,9)."""
     lib = _lib.load()
     for n_, t_ in (("hm", hm), ("center", center), ("center_z", center_z), ("dim", dim), ("rot", rot)):
         _need(t_, torch.float32, n_)
     _need(label_map, torch.int32, "label_map")
+    _need(vel, torch.float32, "vel")
     B, C, H, W = [int(v) for v in hm.shape]
     K = int(K)
     dev = hm.device
-    boxes = torch.empty((B, K, 7), dtype=torch.float32, device=dev)
+    boxes = torch.empty((B, K, 7 if vel is None else 9), dtype=torch.float32, device=dev)
     scores = torch.empty((B, K), dtype=torch.float32, device=dev)
     labels = torch.empty((B, K), dtype=torch.int32, device=dev)
     counts = torch.empty((B,), dtype=torch.int32, device=dev)
@@ -755,11 +757,11 @@ def centerhead_decode_nms(hm, center, center_z, dim, rot, K, feature_map_stride,
     ws = _ws(nbytes, dev)
     lim = (ctypes.c_float * 6)(*[float(v) for v in post_center_limit_range])
     with _Scope("centerhead_decode_nms", B=B, C=C, H=H, W=W, K=K):
-        check(lib.comb_centerhead_decode_nms(
-            _p(hm), _p(center), _p(center_z), _p(dim), _p(rot), B, C, H, W, K, float(feature_map_stride),
+        check(lib.comb_centerhead_decode_nms_vel(
+            _p(hm), _p(center), _p(center_z), _p(dim), _p(rot), _p(vel), B, C, H, W, K, float(feature_map_stride),
             float(voxel_size[0]), float(voxel_size[1]), float(point_cloud_range[0]), float(point_cloud_range[1]), lim,
             float(score_thresh), _p(label_map), float(nms_thresh), int(nms_pre_max), int(nms_post_max), _p(boxes),
-            _p(scores), _p(labels), _p(counts), _p(ws), nbytes, _stream()), "comb_centerhead_decode_nms")
+            _p(scores), _p(labels), _p(counts), _p(ws), nbytes, _stream()), "comb_centerhead_decode_nms_vel")
     return boxes, scores, labels, counts
 
 

@@ -17,15 +17,14 @@ def supported(head):
     """Configurations the fused kernel covers; anything else keeps the reference method."""
     try:
         cfg = head.model_cfg.POST_PROCESSING
-        return (cfg.NMS_CONFIG.NMS_TYPE == "nms_gpu" and int(cfg.MAX_OBJ_PER_SAMPLE) <= MAX_K
-                and "vel" not in head.separate_head_cfg.HEAD_ORDER)
+        return cfg.NMS_CONFIG.NMS_TYPE == "nms_gpu" and int(cfg.MAX_OBJ_PER_SAMPLE) <= MAX_K
     except AttributeError:
         return False
 
 
 def generate_predicted_boxes(head, batch_size, pred_dicts):
-    """Same arguments and return value as the reference method: a list (one dict per frame) of pred_boxes (n,7),
-    pred_scores (n,), pred_labels (n,) int64 1-based."""
+    """Same arguments and return value as the reference method: a list (one dict per frame) of pred_boxes (n,7) — (n,9)
+    for heads with a 'vel' branch (center_head.py:280) —, pred_scores (n,), pred_labels (n,) int64 1-based."""
     cfg = head.model_cfg.POST_PROCESSING
     nms = cfg.NMS_CONFIG
     K = int(cfg.MAX_OBJ_PER_SAMPLE)
@@ -37,7 +36,8 @@ def generate_predicted_boxes(head, batch_size, pred_dicts):
             hm, pd["center"].detach().float().contiguous(), pd["center_z"].detach().float().contiguous(),
             pd["dim"].detach().float().contiguous(), pd["rot"].detach().float().contiguous(), K,
             head.feature_map_stride, head.voxel_size, head.point_cloud_range, cfg.POST_CENTER_LIMIT_RANGE,
-            cfg.SCORE_THRESH, nms.NMS_THRESH, nms.NMS_PRE_MAXSIZE, nms.NMS_POST_MAXSIZE, label_map=label_map))
+            cfg.SCORE_THRESH, nms.NMS_THRESH, nms.NMS_PRE_MAXSIZE, nms.NMS_POST_MAXSIZE, label_map=label_map,
+            vel=pd["vel"].detach().float().contiguous() if "vel" in head.separate_head_cfg.HEAD_ORDER else None))
     counts = torch.stack([o[3] for o in outs]).tolist()                  # the one host read: [head][frame]
     ret = []
     for k in range(batch_size):

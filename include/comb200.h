@@ -338,6 +338,17 @@ int comb_centerhead_decode_nms(const float* hm, const float* center, const float
                                float* out_scores, int* out_labels, int* out_counts, void* workspace,
                                size_t workspace_bytes, void* stream);
 
+/* Heads with a velocity branch ('vel' in SEPARATE_HEAD_CFG.HEAD_ORDER: tools/cfgs/nuscenes_models/cbgs_*_centerpoint.yaml,
+ * tools/cfgs/waymo_models/centerpoint_4frames.yaml; centernet_utils.py:241-245): vel [B,2,H,W] is gathered at the top-K
+ * cells and rides through mask / NMS / gather as columns 7..8 — out_boxes is then [B,K,9]; the NMS itself sees the first
+ * seven columns (model_nms_utils.py:13 boxes_for_nms[:, 0:7]).  vel == NULL is comb_centerhead_decode_nms. */
+int comb_centerhead_decode_nms_vel(const float* hm, const float* center, const float* center_z, const float* dim,
+                                   const float* rot, const float* vel, int B, int C, int H, int W, int K, float stride,
+                                   float vx, float vy, float rx, float ry, const float* limit_range, float score_thresh,
+                                   const int* label_map, float nms_thresh, int nms_pre_max, int nms_post_max,
+                                   float* out_boxes, float* out_scores, int* out_labels, int* out_counts,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- f4: the BEV tensor in channels-last bf16 -------------------------------------------------------------------------
  * HeightCompression (pcdet/models/backbones_2d/map_to_bev/height_compression.py:21-24: dense() + view(N, C*D, H, W))
  * for a 2D backbone (pcdet/models/backbones_2d/base_bev_backbone.py:81-112) that runs in bf16 NHWC: the rows are

@@ -115,6 +115,38 @@ def test_fwd_bf16_epilogue_and_device_count():
     assert (got[no - 77:] == -7.0).all()                # rows beyond the device-side count are untouched
 
 
+@pytest.mark.parametrize("Cin,Cout,ks,n", [(64, 64, (3, 3, 3), 13000), (128, 128, (3, 3, 3), 13000), (64, 128, (3, 3, 3), 9000),
+                                           (128, 128, (3, 1, 1), 13000), (128, 64, (3, 3, 3), 2000), (64, 64, (1, 1, 3), 500)])
+def test_ts_single_tile_passes_split_k(Cin, Cout, ks, n):
+    """Fewer row tiles than SMs (level 4 of the bench frames: 101 tiles): every pass of conv_ts is a single-tile pass and
+    its K range is split over the two halves of the pipeline (two accumulators summed in the epilogue, the streamed-weight
+    ring interleaved).  Streamed (27 taps) and resident (3 taps) weight images, odd and even stage counts, the full
+    epilogue (affine + residual + ReLU) and a device-side row count that cuts the last tile."""
+    rng = np.random.default_rng(Cin + 3 * Cout + n)
+    coords = random_coords(rng, n, 4, [16, 48, 48])
+    nbr = oracle.subm_nbrmap(coords, [16, 48, 48], ks)
+    K = int(np.prod(ks))
+    feats = rng.normal(size=(len(coords), Cin)).astype(np.float32)
+    W = (rng.normal(size=(Cout, K, Cin)) / np.sqrt(K * Cin)).astype(np.float32)
+    no = nbr.shape[1]
+    assert no == n and no < 148 * 128
+    cut = 57
+    scale, shift = [rng.normal(size=(Cout,)).astype(np.float32) for _ in range(2)]
+    res = bf16_round(rng.normal(size=(no, Cout)).astype(np.float32))
+    want = np.maximum(oracle.fast_conv_fwd(bf16_round(feats), bf16_round(W), nbr).astype(np.float64) * scale + shift + res, 0)
+    x = ops.cast_pad(cuda(feats), Cin)
+    wp = ops.pack_weight_bf16(cuda(W))
+    out = torch.full((no, Cout), -7.0, dtype=torch.float32, device="cuda")
+    ops.spconv_fwd_bf16(x, wp, K, Cout, cuda(nbr), scale=cuda(scale), shift=cuda(shift), residual=cuda(res).to(torch.bfloat16),
+                        relu=True, no_dev=torch.tensor([no - cut], dtype=torch.int32, device="cuda"), out=out)
+    got = out.cpu().numpy()
+    assert rel_err(got[: no - cut], want[: no - cut].astype(np.float32)) < 1e-4
+    assert (got[no - cut:] == -7.0).all()
+    plain = ops.spconv_fwd_bf16(x, wp, K, Cout, cuda(nbr), out_dtype=torch.float32)
+    again = ops.spconv_fwd_bf16(x, wp, K, Cout, cuda(nbr), out_dtype=torch.float32)
+    assert torch.equal(plain, again)                    # fixed summation order: bit-reproducible
+
+
 @pytest.mark.parametrize("C,n", [(16, 50000), (32, 50000), (64, 90000), (128, 90000)])
 def test_bf16_many_tiles_persistent_loop(C, n):
     """More (super-)tiles than SMs: every CTA walks several of them (slot / weight-stage / accumulator / index
@@ -212,7 +244,8 @@ def test_module_autograd_matches_oracle():
 
 
 @pytest.mark.parametrize("env", [{"COMB_CONV_IMPL": "ss"}, {"COMB_CONV_IMPL": "ts"}, {"COMB_CONV_IMPL": "tr"}, {"COMB_PDL": "1"},
-                                 {"COMB_CONV_IMPL": "ts", "COMB_TS_BLOCKED": "1", "COMB_TS_NI": "8", "COMB_TS_NB": "8"}])
+                                 {"COMB_CONV_IMPL": "ts", "COMB_TS_BLOCKED": "1", "COMB_TS_NI": "8", "COMB_TS_NB": "8"},
+                                 {"COMB_CONV_IMPL": "ts", "COMB_TS_SPLIT": "0"}, {"COMB_CONV_IMPL": "ts", "COMB_TS_NB": "3"}])
 def test_alternate_conv_kernels_stay_correct(env):
     """The documented A/B switches (shared-memory-A tcgen05 kernel; conv_ts or conv_tr forced for every layer shape;
     programmatic dependent launch; blocked tile assignment with deep rings) are read once per process, so each is
