@@ -52,3 +52,23 @@ ops.comloss_reweight(pred, rmap, mask.clone(), torch.ones_like(hm), 0.05, -10.0,
 ops.comaug_valid_mask(synth.make_clustered_boxes(40, seed=1), synth.make_boxes(60, seed=2))
 torch.cuda.synchronize()
 print("r2 kernels ok: conv_tr rows %d, targets %d" % (int(y.shape[0]), int(mask.sum())))
+
+# late r2: conv_ts with streamed weights — full two-tile passes followed by split single-tile passes (two accumulators,
+# interleaved weight ring) at 64x64, and a resident-weight split pass at 128x128 K=3; the velocity-head decode
+n3 = 150 * 128 * 2 + 700                                     # 148 full passes, then a wave of single-tile passes
+nb3 = torch.randint(-1, n3, (27, n3), device="cuda", dtype=torch.int32)
+nb3[nb3 % 3 != 0] = -1
+f64 = ops.cast_pad(torch.randn((n3, 64), device="cuda"), 64)
+y3 = ops.spconv_fwd_bf16(f64, ops.pack_weight_bf16(torch.randn((64, 27, 64), device="cuda") / 40), 27, 64, nb3)
+n4 = 3000
+nb4 = torch.randint(-1, n4, (3, n4), device="cuda", dtype=torch.int32)
+f128 = ops.cast_pad(torch.randn((n4, 128), device="cuda"), 128)
+y4 = ops.spconv_fwd_bf16(f128, ops.pack_weight_bf16(torch.randn((128, 3, 128), device="cuda") / 20), 3, 128, nb4)
+hmv = torch.randn((2, 3, 64, 64), device="cuda") - 2.0
+bv = ops.centerhead_decode_nms(hmv, torch.rand((2, 2, 64, 64), device="cuda"), torch.zeros((2, 1, 64, 64), device="cuda"),
+                               torch.zeros((2, 3, 64, 64), device="cuda"), torch.randn((2, 2, 64, 64), device="cuda"), 100, 8,
+                               [0.1, 0.1, 0.15], [-25.6, -25.6, -2, 25.6, 25.6, 4], [-30, -30, -5, 30, 30, 5], 0.1, 0.7, 4096, 83,
+                               label_map=torch.arange(3, dtype=torch.int32, device="cuda"),
+                               vel=torch.randn((2, 2, 64, 64), device="cuda"))
+torch.cuda.synchronize()
+print("late r2 kernels ok: conv_ts rows %d + %d, decode counts %s" % (int(y3.shape[0]), int(y4.shape[0]), bv[3].tolist()))
