@@ -116,3 +116,38 @@ def test_round2_hooks_attach_and_leave_cpu_tensors_to_the_reference():
         d = 2 * r + 1
         want = torch.from_numpy(cu.gaussian2D((d, d), sigma=d / 6)).float().numpy()
         assert tab.dtype == np.float32 and np.array_equal(tab, want), r
+
+
+def test_fused_postprocessing_coverage_rule():
+    """Which CenterHead configurations the fused decode + NMS covers (everything else keeps the reference method):
+    rotated `nms_gpu`, at most 1024 candidates per frame; heads with a velocity branch included (nine-column boxes)."""
+    import types
+    from com_b200.pcdet_ops import center_decode
+    E = ref_py.EasyDict
+
+    def head(nms_type="nms_gpu", K=500, order=("center", "center_z", "dim", "rot")):
+        cfg = E(POST_PROCESSING=E(MAX_OBJ_PER_SAMPLE=K, NMS_CONFIG=E(NMS_TYPE=nms_type)))
+        return types.SimpleNamespace(model_cfg=cfg, separate_head_cfg=E(HEAD_ORDER=list(order)))
+
+    assert center_decode.supported(head())
+    assert center_decode.supported(head(order=("center", "center_z", "dim", "rot", "vel")))      # nuScenes / 4-frame Waymo
+    assert not center_decode.supported(head(nms_type="circle_nms"))
+    assert not center_decode.supported(head(K=4096))
+    assert not center_decode.supported(types.SimpleNamespace(model_cfg=E()))                       # no POST_PROCESSING
+    # every reference config with a CenterHead falls on one side of the rule without raising
+    import glob
+    import os
+    import yaml
+    root = os.path.join(ref_py.REF, "tools", "cfgs")
+    if os.path.isdir(root):                                   # only where the reference tree is present (this container)
+        seen = 0
+        for f in sorted(glob.glob(os.path.join(root, "*_models", "*.yaml"))):
+            y = yaml.safe_load(open(f))
+            dh = (y.get("MODEL") or {}).get("DENSE_HEAD") or {}
+            if "CenterHead" not in str(dh.get("NAME", "")) or "POST_PROCESSING" not in dh:
+                continue
+            pp = dh["POST_PROCESSING"]
+            h = head(pp["NMS_CONFIG"]["NMS_TYPE"], pp["MAX_OBJ_PER_SAMPLE"], dh["SEPARATE_HEAD_CFG"]["HEAD_ORDER"])
+            assert center_decode.supported(h) == (pp["NMS_CONFIG"]["NMS_TYPE"] == "nms_gpu" and pp["MAX_OBJ_PER_SAMPLE"] <= 1024), f
+            seen += 1
+        assert seen >= 5
