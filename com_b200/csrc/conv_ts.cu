@@ -55,6 +55,7 @@ constexpr int kMaxK = 32;
 constexpr int kMaxBStages = 8;
 constexpr int kSmemBudget = 225 * 1024;
 constexpr int kBResidentMax = 160 * 1024;
+constexpr bool kWideDefault = true;    // COMB_TS_WIDE unset: one 32-byte load per row (0: the two 16-byte pieces of r1)
 
 template <int CIN, int COUT>
 struct TsCfg {
@@ -131,6 +132,16 @@ template <int PIPE>
 __device__ __forceinline__ void wait_bg(uint32_t bar, uint32_t parity) {
   if (PIPE == 2) mbar_wait(bar, parity);
   else mbar_wait_sleep(bar, parity);
+}
+
+// 256 zero bytes: the "feature row" of an absent neighbour in the wide-load gather (PIPE == 3)
+__device__ __align__(256) uint4 g_ts_zero_row[16];
+
+// 32 bytes of a feature row (read-only path), as the two 16-byte halves the tcgen05.st fragment wants
+__device__ __forceinline__ void ldg256(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
 }
 
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -399,6 +410,20 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
       eo0 = 8 * j;
       eo1 = 32 + 8 * j;
     }
+    // WIDE (PIPE == 3, late r2): ONE 32-byte load per row instead of two 16-byte pieces 64 bytes apart.  Lane j of a row's
+    // four lanes reads bytes 32j..32j+31 of the 128-byte chunk row, so a warp request covers 8 rows x 128 contiguous
+    // bytes = 8 full lines: half the load instructions and half the L1 data-pipe wavefronts per byte (ncu of the r2
+    // kernels: l1tex__data_pipe_lsu_wavefronts is the busiest unit of the gather, 43 % at 64x64, 74 % in conv_tr<32,32>).
+    // An absent neighbour reads a zero row instead of predicating and zero-filling 8 registers.  The K permutation
+    // changes with it (source element 16j + w -> K position 16*(w/4) + 4j + w%4; ts_pack_weight mode 2).
+    // Same-box A/B on the bench frames, two runs each (profiles/r2_bench_wide{0,1}.json): 64x64 65.3 -> 64.0 us per launch,
+    // 128x128 45.0 -> 44.5, step 1.0725 -> 1.0682 ms — small (these layers are latency-bound, their L1 data pipe was at
+    // 43 / 27 %), consistent, and fewer instructions: the default.  Forcing conv_ts on the narrow levels stays slower
+    // than conv_tr (16x16 42 vs 32 us, 32x32 65 vs 60).
+    constexpr bool WIDE = PIPE == 3;
+    const int slotw = CIN <= 64 ? (16 * j) / CIN : 0;
+    const int eow = CIN <= 64 ? (16 * j) % CIN : 16 * j;
+    const char* zrow = reinterpret_cast<const char*>(g_ts_zero_row);
     const __nv_bfloat16* in = p.in;
     const bool tr = q == 0 && grp == 0 && lane == 0;
     int s = 0, gst = 0;
@@ -439,6 +464,13 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
 #pragma unroll
               for (int rr = 0; rr < 2; ++rr) {
                 const int row = q * 32 + h * 16 + rr * 8 + r8;
+                if (WIDE) {
+                  int rw;
+                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw) : "r"(idx_c + (uint32_t)(slotw * kBM + row) * 4) : "memory");
+                  const void* src = rw >= 0 ? reinterpret_cast<const char*>(in + (size_t)(uint32_t)rw * CIN + ehalf + eow) : zrow;
+                  ldg256(src, v[h][rr][0], v[h][rr][1]);
+                  continue;
+                }
                 int rw0, rw1;
                 asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rw0) : "r"(idx_c + (uint32_t)(slot0 * kBM + row) * 4) : "memory");
                 if (CIN <= 32) {
@@ -765,7 +797,8 @@ __global__ void __launch_bounds__(256) ts_pack_kernel(const float* __restrict__ 
     const int n = (int)((i / kChunkK) % Cout);
     const int c = (int)(i / ((long long)kChunkK * Cout));
     const int half = kappa >> 5, wq = (kappa >> 4) & 1, j = (kappa >> 2) & 3, wl = kappa & 3;
-    const int e = natural ? kappa : 8 * (4 * half + j) + 4 * wq + wl;        // source element of the chunk row
+    // source element of the chunk row: natural order (1), the wide-load fragment order (2) or the two-piece order (0)
+    const int e = natural == 1 ? kappa : natural == 2 ? 16 * j + 4 * (kappa >> 4) + wl : 8 * (4 * half + j) + 4 * wq + wl;
     int k, ci;
     if constexpr (CIN <= 64) {
       k = c * (64 / CIN) + e / CIN;
@@ -786,10 +819,14 @@ static int ts_pipe() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("COMB_TS_PIPE");
-    v = e ? atoi(e) : 0;      // 0 (default): r1 loop; 1: pipelined gather; 2: sleep-free background waits
+    v = e ? atoi(e) : 0;      // 0: r1 loop; 1: pipelined gather; 2: sleep-free background waits
 #ifndef COMB_TS_EXPERIMENTS
     v = 0;                    // the variants are not part of the product library (nvcc -DCOMB_TS_EXPERIMENTS builds them)
 #endif
+    if (v == 0) {             // 3: the r1 loop with one 32-byte load per row (COMB_TS_WIDE, see the gather)
+      const char* w = getenv("COMB_TS_WIDE");
+      if (w ? atoi(w) != 0 : kWideDefault) v = 3;
+    }
   }
   return v;
 }
@@ -833,6 +870,8 @@ int launch_ts(const ConvFwdArgs& p_in, cudaStream_t stream) {
   if (configured.first()) {
     COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
     COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
 #ifdef COMB_TS_EXPERIMENTS
     COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
     COMB_CUDA(cudaFuncSetAttribute(spconv_ts_kernel<CIN, COUT, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
@@ -848,7 +887,9 @@ int launch_ts(const ConvFwdArgs& p_in, cudaStream_t stream) {
   p.split = split_env;
   const int ntiles_max = cdiv(p.no_max, kBM);
   const int grid = ntiles_max < sm_count() ? ntiles_max : sm_count();
-  if (p.dbg != nullptr) COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, true, 0>, grid, kThreads, smem, stream, p));   // pipeline trace build
+  if (p.dbg != nullptr && ts_pipe() == 3) COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, true, 3>, grid, kThreads, smem, stream, p));
+  else if (p.dbg != nullptr) COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, true, 0>, grid, kThreads, smem, stream, p));   // pipeline trace build
+  else if (ts_pipe() == 3) COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, false, 3>, grid, kThreads, smem, stream, p));
 #ifdef COMB_TS_EXPERIMENTS     // the two measured-and-rejected gather variants (software-pipelined gather, sleep-free waits): built on demand only
   else if (ts_pipe() == 1) COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, false, 1>, grid, kThreads, smem, stream, p));
   else if (ts_pipe() == 2) COMB_CUDA(launch_pdl(spconv_ts_kernel<CIN, COUT, false, 2>, grid, kThreads, smem, stream, p));
@@ -889,7 +930,8 @@ int ts_pack_weight(const float* weight, int Cout, int K, int Cin, int Cin_p, int
   const long long total = (long long)nchunks * Cout * kChunkK;
   const int grid = cdiv(total, 256);
   __nv_bfloat16* out = (__nv_bfloat16*)wpacked;
-  const int natural = (natural_in || ts_pipe() == 1) ? 1 : 0;   // the pipelined gather keeps K in its natural order
+  // the pipelined gather (and conv_tr) keep K in its natural order; the wide-load gather has its own fragment order
+  const int natural = (natural_in || ts_pipe() == 1) ? 1 : ts_pipe() == 3 ? 2 : 0;
   switch (Cin_p) {
     case 16: ts_pack_kernel<16><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, natural, out); break;
     case 32: ts_pack_kernel<32><<<grid, 256, 0, stream>>>(weight, Cout, K, Cin, nchunks, natural, out); break;

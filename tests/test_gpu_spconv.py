@@ -245,7 +245,8 @@ def test_module_autograd_matches_oracle():
 
 @pytest.mark.parametrize("env", [{"COMB_CONV_IMPL": "ss"}, {"COMB_CONV_IMPL": "ts"}, {"COMB_CONV_IMPL": "tr"}, {"COMB_PDL": "1"},
                                  {"COMB_CONV_IMPL": "ts", "COMB_TS_BLOCKED": "1", "COMB_TS_NI": "8", "COMB_TS_NB": "8"},
-                                 {"COMB_CONV_IMPL": "ts", "COMB_TS_SPLIT": "0"}, {"COMB_CONV_IMPL": "ts", "COMB_TS_NB": "3"}])
+                                 {"COMB_CONV_IMPL": "ts", "COMB_TS_SPLIT": "0"}, {"COMB_CONV_IMPL": "ts", "COMB_TS_NB": "3"},
+                                 {"COMB_CONV_IMPL": "ts", "COMB_TS_WIDE": "1"}, {"COMB_CONV_IMPL": "ts", "COMB_TS_WIDE": "0"}])
 def test_alternate_conv_kernels_stay_correct(env):
     """The documented A/B switches (shared-memory-A tcgen05 kernel; conv_ts or conv_tr forced for every layer shape;
     programmatic dependent launch; blocked tile assignment with deep rings) are read once per process, so each is
