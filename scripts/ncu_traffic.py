@@ -22,6 +22,13 @@ WANT = {
     "smsp__inst_executed.sum": "warp_instructions",
     "launch__registers_per_thread": "registers",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
+    # the gather's real ceiling: wavefronts through the L1 data pipe (one per distinct line of a warp request) and the
+    # register write-back of the loaded rows
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "l1_data_pipe_lsu_wavefronts_pct",
+    "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed": "l1_lsu_writeback_active_pct",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum": "global_load_requests",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum": "global_load_sectors",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard_per_issue",
 }
 UNIT = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "us": 1.0, "ms": 1e3, "ns": 1e-3}
 
