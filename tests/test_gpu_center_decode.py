@@ -59,7 +59,7 @@ def same_detections(g, w, vel=False):
     tied[:-1] |= eq
     differ = (g["pred_labels"] != w["pred_labels"]) | ((g["pred_boxes"] - w["pred_boxes"]).abs() > 1e-5).any(dim=1)
     assert not bool((differ & ~tied).any()), "order differs outside runs of equal scores"
-    assert int(differ.sum()) <= 4
+    assert int(differ.sum()) <= 8                      # a handful of swapped pairs at most
 
     def canon(d):
         b = d["pred_boxes"].double().cpu().numpy()
