@@ -412,8 +412,10 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_ts_kernel(ConvFwdArgs p) {
     }
     // WIDE (PIPE == 3, late r2): ONE 32-byte load per row instead of two 16-byte pieces 64 bytes apart.  Lane j of a row's
     // four lanes reads bytes 32j..32j+31 of the 128-byte chunk row, so a warp request covers 8 rows x 128 contiguous
-    // bytes = 8 full lines: half the load instructions and half the L1 data-pipe wavefronts per byte (ncu of the r2
-    // kernels: l1tex__data_pipe_lsu_wavefronts is the busiest unit of the gather, 43 % at 64x64, 74 % in conv_tr<32,32>).
+    // bytes = 8 full lines and half the load instructions.  (The hoped-for halving of the L1 data-pipe wavefronts per
+    // byte — l1tex__data_pipe_lsu_wavefronts is the busiest unit of the gather, 43 % at 64x64, 74 % in conv_tr<32,32> —
+    // did not happen: ncu counts 15.5 wavefronts per LDG.256 request against 8.7 per LDG.128 request, the 32-byte load
+    // is served in two 16-byte phases; profiles/r2wide_ncu_summary.json.)
     // An absent neighbour reads a zero row instead of predicating and zero-filling 8 registers.  The K permutation
     // changes with it (source element 16j + w -> K position 16*(w/4) + 4j + w%4; ts_pack_weight mode 2).
     // Same-box A/B on the bench frames, two runs each (profiles/r2_bench_wide{0,1}.json): 64x64 65.3 -> 64.0 us per launch,
